@@ -1,0 +1,100 @@
+"""Generate tests/golden/*.npz by running the REFERENCE's own Python on CPU.
+
+Run in the build container only (needs /root/reference; the GPU box does not have it):
+
+    python tests/golden/make_golden.py
+
+The reference module ``awq.quantize.qmodule`` does ``import awq_inference_engine`` at
+import time (qmodule.py:4); a stub module is registered for that name because only the
+pure-PyTorch / numpy packer code is exercised here (no kernel is called).
+The fixtures pin oracle/w4a16_oracle.py (pack layout, buffer shapes, from_linear,
+quantiser formulas); the reference has no golden vectors of its own.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = os.environ.get("AWQ_REFERENCE", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _import_reference():
+    sys.modules.setdefault("awq_inference_engine", types.ModuleType("awq_inference_engine"))
+    # awq/quantize/__init__.py pulls in w8a8_linear / smooth; import the two files directly
+    import importlib.util
+
+    def load(name, rel):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(REF, rel))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
+
+    qmodule = load("ref_qmodule", "awq/quantize/qmodule.py")
+    # quantizer.py has package-relative imports at module top; extract the one function
+    src = open(os.path.join(REF, "awq/quantize/quantizer.py")).read()
+    start = src.index("def pseudo_quantize_tensor(")
+    end = src.index("@torch.no_grad()", start)
+    ns = {"torch": torch}
+    exec(compile(src[start:end], "ref_quantizer_excerpt", "exec"), ns)
+    return qmodule, ns["pseudo_quantize_tensor"]
+
+
+def main():
+    qmodule, pseudo_quantize_tensor = _import_reference()
+    g = torch.Generator().manual_seed(20260922)
+    out = {}
+
+    # 1. pack_intweight on random nibbles, several shapes (incl. 11008-style non-pow2 K)
+    for idx, (N, K) in enumerate([(4, 64), (8, 128), (16, 256), (32, 192), (64, 512), (128, 1024)]):
+        q = torch.randint(0, 16, (N, K), generator=g, dtype=torch.int32)
+        packed = qmodule.pack_intweight(q, interleave=4, kstride=64)
+        out[f"pack{idx}_q"] = q.numpy().astype(np.uint8)
+        out[f"pack{idx}_packed"] = packed.numpy()
+
+    # 2. calculate_zeros_width table
+    ins = [64, 128, 256, 1024, 3584, 4096, 5120, 8192, 11008, 14336, 28672]
+    out["zw_in"] = np.array(ins)
+    out["zw_g128"] = np.array([qmodule.calculate_zeros_width(i, 128) for i in ins])
+    out["zw_g64"] = np.array([qmodule.calculate_zeros_width(i, 64) for i in ins])
+
+    # 3. pseudo_quantize_tensor + WQLinear.from_linear, fp32 / fp16 / bf16 layers
+    for tag, dt in (("f32", torch.float32), ("f16", torch.float16), ("bf16", torch.bfloat16)):
+        N, K, G = 32, 256, 128
+        lin = torch.nn.Linear(K, N, bias=True)
+        with torch.no_grad():
+            lin.weight.copy_(torch.randn(N, K, generator=g) * 0.02)
+            lin.bias.copy_(torch.randn(N, generator=g) * 0.1)
+        lin = lin.to(dt)
+        w0 = lin.weight.data.clone()
+        w_dq, scales, zeros = pseudo_quantize_tensor(
+            lin.weight.data.clone(), n_bit=4, zero_point=True, q_group_size=G, get_scale_zp=True)
+        lin.weight.data = w_dq            # real_quantize_model_weight does the same (quantizer.py:150-152)
+        wq = qmodule.WQLinear.from_linear(lin, 4, G, False, scales, zeros)
+        f = lambda t: t.detach().float().numpy()
+        out[f"fl_{tag}_w0"] = f(w0)
+        out[f"fl_{tag}_wdq"] = f(w_dq)
+        out[f"fl_{tag}_scales"] = f(scales)
+        out[f"fl_{tag}_zeros"] = f(zeros)
+        out[f"fl_{tag}_qweight"] = wq.qweight.numpy()
+        out[f"fl_{tag}_sbuf"] = f(wq.scales)
+        out[f"fl_{tag}_zbuf"] = f(wq.scaled_zeros)
+        out[f"fl_{tag}_bias"] = f(wq.bias)
+        assert tuple(wq.qweight.shape) == (N // 4, K) and wq.qweight.dtype == torch.int16
+
+    # 4. buffer shapes declared by WQLinear.__init__ for the BASELINE shapes
+    shapes = []
+    for (K, N) in [(4096, 4096), (4096, 6144), (4096, 14336), (14336, 4096), (8192, 1280),
+                   (1024, 8192), (8192, 3584), (3584, 8192), (11008, 4096)]:
+        m = qmodule.WQLinear(4, 128, K, N, False, "cpu")
+        shapes.append([K, N, *m.qweight.shape, *m.scales.shape, *m.scaled_zeros.shape])
+    out["init_shapes"] = np.array(shapes)
+
+    np.savez_compressed(os.path.join(HERE, "reference_packer.npz"), **out)
+    print("wrote", os.path.join(HERE, "reference_packer.npz"), len(out), "arrays")
+
+
+if __name__ == "__main__":
+    main()

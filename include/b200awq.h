@@ -1,0 +1,95 @@
+/*
+ * b200awq.h — C ABI of the B200-native W4A16 (AWQ v2 layout) quantized-linear path.
+ *
+ * This is the drop-in boundary: the two launchers below are what the reference's
+ * extension entry points bind to,
+ *
+ *   gemv_forward_cuda_new(in_feats, kernel, scaling_factors, zeros, m, n, k, group_size)
+ *       reference: awq/kernels/csrc/quantization_new/gemv/gemv_cuda.h:4-12,
+ *                  host code gemv_cuda.cu:245-338, exported at csrc/pybind.cpp:23
+ *   gemm_forward_cuda_new(in_feats, kernel, scales, zeros)
+ *       reference: awq/kernels/csrc/quantization_new/gemm/gemm_cuda.h:3,
+ *                  host code gemm_cuda.cu:1126-1236, exported at csrc/pybind.cpp:22
+ *
+ * called from awq/quantize/qmodule.py:207,218 (WQLinear.forward) and
+ * tinychat/modules/fused_mlp.py:40,51,65,72.
+ *
+ * Conventions: plain pointers and sizes, no torch types.  All pointers are DEVICE
+ * pointers.  Inputs are borrowed for the duration of the (asynchronous) launch; nothing
+ * is retained, nothing is allocated, the calling thread is never synchronised with the
+ * device.  Work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy
+ * default stream).  Return value: 0 on success, a negative B200AWQ_ERR_* for rejected
+ * arguments (nothing was launched), or a positive cudaError_t if the launch failed.
+ *
+ * Tensor layouts (exactly the reference's WQLinear buffers, awq/quantize/qmodule.py:98-137):
+ *   x        [m, k]            fp16 / bf16, row-major, 16-byte aligned
+ *   qweight  [n/4, k]          int16, the interleaved 4-bit packing of pack_intweight
+ *                              (qmodule.py:26-65), 16-byte aligned
+ *   scales   [>= k/group, n]   same dtype as x; rows beyond k/group are padding
+ *   szeros   [>= k/group, n]   same dtype as x  (= -scale * zero_point, qmodule.py:194-196)
+ *   y        [m, n]            same dtype as x, row-major
+ * Semantics: y[i,j] = sum_k x[i,k] * rn_T( q[j,k] * scales[k/group, j] + szeros[k/group, j] )
+ * with q the unsigned nibble 0..15, accumulated in fp32, rounded once to T.
+ */
+#ifndef B200AWQ_H_
+#define B200AWQ_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200AWQ_DTYPE_F16 0
+#define B200AWQ_DTYPE_BF16 1
+
+#define B200AWQ_OK 0
+#define B200AWQ_ERR_SHAPE (-1)     /* n % 8 (gemv) / n % 128 (gemm), k % 128, m out of range */
+#define B200AWQ_ERR_GROUP (-2)     /* group_size != 128 (reference: gemv_cuda.cu:289,332-335) */
+#define B200AWQ_ERR_ALIGN (-3)     /* a pointer is NULL or not 16-byte aligned */
+#define B200AWQ_ERR_DTYPE (-4)     /* dtype is not F16 / BF16 (reference: dispatch_utils.cuh:7-18) */
+#define B200AWQ_ERR_BATCH (-5)     /* gemv with m outside 1..7 (reference: gemv_cuda.cu:291-330) */
+#define B200AWQ_ERR_WORKSPACE (-6) /* workspace smaller than b200awq_w4a16_gemm_workspace_bytes */
+#define B200AWQ_ERR_DRIVER (-7)    /* CUDA driver entry point for TMA descriptors unavailable */
+#define B200AWQ_ERR_DEVICE (-8)    /* current device is not compute capability 10.x */
+
+/* Decode path: 1 <= m <= 7 (the reference's GEMV envelope).  n % 8 == 0, k % 128 == 0,
+ * group_size == 128. */
+int b200awq_w4a16_gemv(const void* x, const void* qweight, const void* scales, const void* szeros,
+                       void* y, int m, int n, int k, int group_size, int dtype, void* stream);
+
+/* Prefill / batched path: any m >= 1.  n % 128 == 0, k % 128 == 0, group 128 (the
+ * reference GEMM hard-codes G = 128, gemm_cuda.cu:1157).  `workspace` may be NULL when
+ * b200awq_w4a16_gemm_workspace_bytes(m, n, k) == 0. */
+int b200awq_w4a16_gemm(const void* x, const void* qweight, const void* scales, const void* szeros,
+                       void* y, int m, int n, int k, int group_size, int dtype,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+size_t b200awq_w4a16_gemm_workspace_bytes(int m, int n, int k);
+
+/* Names used by BASELINE.json's north_star; identical to the two launchers above. */
+int gemv_forward_4bit(const void* x, const void* qweight, const void* scales, const void* szeros,
+                      void* y, int m, int n, int k, int group_size, int dtype, void* stream);
+int gemm_forward_4bit(const void* x, const void* qweight, const void* scales, const void* szeros,
+                      void* y, int m, int n, int k, int group_size, int dtype,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* Programmatic dependent launch between consecutive launches of this library on one
+ * stream (weights of launch i+1 are prefetched while launch i drains).  Default on;
+ * B200AWQ_PDL=0 in the environment or b200awq_set_pdl(0) turns it off.  Returns the
+ * previous setting. */
+int b200awq_set_pdl(int enable);
+
+/* Number of kernels this library has launched since load (monotonic, per process). */
+unsigned long long b200awq_launch_count(void);
+
+/* Human-readable text for a return value of the functions above. */
+const char* b200awq_strerror(int code);
+
+/* "b200awq <version> sm_100a" */
+const char* b200awq_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200AWQ_H_ */

@@ -95,11 +95,23 @@ def pack_intweight(q: np.ndarray) -> np.ndarray:
 
 
 def unpack_intweight(qweight: np.ndarray) -> np.ndarray:
-    """int16 [N//4, K] -> q[N, K] uint8 in 0..15 (inverse of pack_intweight)."""
+    """int16 [N//4, K] -> q[N, K] uint8 in 0..15 (inverse of pack_intweight).
+
+    Structured form of packed_index(): P[r, 64*tile + 16*row + 8*blk + 2*u + hi] nibble j
+    is q[4r + row, 64*tile + 32*blk + 8*j + 2*u + hi]."""
     P = np.ascontiguousarray(qweight).view(np.uint16)
     R, K = P.shape
-    N = R * 4
-    nn, kk = np.meshgrid(np.arange(N), np.arange(K), indexing="ij")
+    a = P.reshape(R, K // 64, 4, 2, 4, 2)                           # r, tile, row, blk, u, hi
+    nib = (a[..., None] >> (4 * np.arange(4, dtype=np.uint16))) & 0xF   # ..., j
+    q = nib.transpose(0, 2, 1, 3, 6, 4, 5)                           # r, row, tile, blk, j, u, hi
+    return np.ascontiguousarray(q).reshape(R * 4, K).astype(np.uint8)
+
+
+def unpack_intweight_indexed(qweight: np.ndarray) -> np.ndarray:
+    """Same as unpack_intweight, through packed_index() (slow; cross-check only)."""
+    P = np.ascontiguousarray(qweight).view(np.uint16)
+    R, K = P.shape
+    nn, kk = np.meshgrid(np.arange(R * 4), np.arange(K), indexing="ij")
     r, c, j = packed_index(nn, kk)
     return ((P[r, c] >> (4 * j).astype(np.uint16)) & 0xF).astype(np.uint8)
 
@@ -135,38 +147,42 @@ def rounder(dtype: str):
 # --------------------------------------------------------------------------------------
 # dequantised weight and forward
 # --------------------------------------------------------------------------------------
-def dequant_weight(qweight, scales, szeros, group_size: int = 128, dtype: str = "f16") -> np.ndarray:
-    """w~[n,k] = rn_T( q[n,k] * S[k//G, n] + Z[k//G, n] ) as float64 [N, K].
+def dequant_weight(qweight, scales, szeros, group_size: int = 128, dtype: str = "f16", rows=None) -> np.ndarray:
+    """w~[n,k] = rn_T( q[n,k] * S[k//G, n] + Z[k//G, n] ) as float64 [N, K] (or [len(rows), K]).
 
     q is the *unsigned* nibble 0..15 (quantization_new/dequantize.cuh:63,69 subtract
     1024 / 64 only, no -8); scale and zero are applied with ONE fused multiply-add in
     the activation dtype (gemv_cuda.cu:161,165; gemm_cuda.cu:306-308,916).
     ``scales``/``szeros`` are the [>=K/G, N] buffers of WQLinear (qmodule.py:109-130);
-    padding rows are ignored.
+    padding rows are ignored.  ``rows`` selects output channels (full-size spot checks).
     """
-    q = unpack_intweight(qweight).astype(np.float64)            # [N, K]
+    q = unpack_intweight(qweight)                                # [N, K] uint8
     N, K = q.shape
     G = group_size
     S = np.asarray(scales, dtype=np.float64)[: K // G].T         # [N, K/G]
     Z = np.asarray(szeros, dtype=np.float64)[: K // G].T
+    if rows is not None:
+        q, S, Z = q[rows], S[rows], Z[rows]
+    q = q.astype(np.float64)
     S = np.repeat(S, G, axis=1)
     Z = np.repeat(Z, G, axis=1)
     return rounder(dtype)(q * S + Z)
 
 
 def wq_linear_forward(x, qweight, scales, szeros, bias=None, group_size: int = 128,
-                      dtype: str = "f16") -> np.ndarray:
+                      dtype: str = "f16", rows=None) -> np.ndarray:
     """Y = X . w~^T (+ bias) in float64 (WQLinear.forward, qmodule.py:201-224).
 
     The reference accumulates in fp16 (GEMV chains gemv_cuda.cu:195-198, fp16 mma
     gemm_cuda.cu:124-131); accumulation order is not part of the contract, so the
     oracle accumulates exactly (float64) and the tests bound ||Y - Y64|| / ||Y64||.
     """
-    w = dequant_weight(qweight, scales, szeros, group_size, dtype)
+    w = dequant_weight(qweight, scales, szeros, group_size, dtype, rows)
     x = np.asarray(x, dtype=np.float64)
     y = x.reshape(-1, x.shape[-1]) @ w.T
     if bias is not None:
-        y = y + np.asarray(bias, dtype=np.float64)
+        b = np.asarray(bias, dtype=np.float64)
+        y = y + (b if rows is None else b[rows])
     return y.reshape(*x.shape[:-1], w.shape[0])
 
 

@@ -84,11 +84,11 @@ int b200awq_w4a16_gemm(const void* x, const void* qweight, const void* scales, c
   if (int e = check_common(x, qweight, scales, szeros, y, m, n, k, group_size, dtype)) return e;
   if (n % 128) return B200AWQ_ERR_SHAPE;  // reference: N / CTA_N with CTA_N = 128, gemm_cuda.cu:38,1225
   const int stream_max_m = env_int("B200AWQ_STREAM_MAX_M", 16);
-  int r;
+  int r = B200AWQ_ERR_SHAPE;
   if (m <= stream_max_m && m <= 16)
     r = b200awq::launch_stream(x, qweight, scales, szeros, y, m, n, k, dtype, pdl_enabled(), stream_tuning(),
                                static_cast<cudaStream_t>(stream));
-  else
+  if (r == B200AWQ_ERR_SHAPE)  // too many tokens for the streaming kernel (or its k slice does not fit on chip)
     r = b200awq::launch_umma(x, qweight, scales, szeros, y, m, n, k, dtype, pdl_enabled(), umma_tuning(),
                              static_cast<cudaStream_t>(stream));
   if (r == 0) g_launches.fetch_add(1, std::memory_order_relaxed);

@@ -48,16 +48,19 @@ def _packed_coords(N, K, device):
 
 
 def pack_intweight(unpacked_qweight, interleave=4, kstride=64):
-    """[N, K] integers (low 4 bits used) -> int16 [N // 4, K] (reference qmodule.py:26-65)."""
+    """[N, K] integers -> int16 [N // 4, K] (reference qmodule.py:26-65).
+
+    Like the reference, the four values of one int16 are OR-ed together UNMASKED
+    (qmodule.py:50-55): integers outside 0..15 spill into the neighbouring nibbles exactly
+    as they do there (from_linear on weights that were not fake-quantised first)."""
     assert interleave == 4 and kstride == 64, "only the reference's (4, 64) interleave exists"
-    q = unpacked_qweight
+    q = unpacked_qweight.to(torch.int32)
     N, K = q.shape
     assert N % 4 == 0 and K % 64 == 0
-    r, c, j = _packed_coords(N, K, q.device)
-    vals = ((q.to(torch.int32) & 0xF) << (4 * j).to(torch.int32)).to(torch.int32)
-    out = torch.zeros(N // 4, K, dtype=torch.int32, device=q.device)
-    out.view(-1).index_add_(0, (r * K + c).reshape(-1), vals.reshape(-1))  # nibbles are disjoint: add == or
-    out = torch.where(out >= 32768, out - 65536, out)
+    # P[r, 64*tile + 16*row + 8*blk + 2*u + hi] nibble j  <-  q[4r + row, 64*tile + 32*blk + 8*j + 2*u + hi]
+    v = q.view(N // 4, 4, K // 64, 2, 4, 4, 2).permute(0, 2, 1, 3, 5, 6, 4).reshape(N // 4, K, 4)
+    out = v[..., 0] | (v[..., 1] << 4) | (v[..., 2] << 8) | (v[..., 3] << 12)
+    out = ((out + 32768) & 0xFFFF) - 32768        # numpy astype("int16") wrap-around (qmodule.py:59)
     return out.to(torch.int16).contiguous()
 
 

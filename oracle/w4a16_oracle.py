@@ -83,15 +83,19 @@ def packed_index(n, k):
 
 
 def pack_intweight(q: np.ndarray) -> np.ndarray:
-    """q[N, K] integers in 0..15  ->  int16 [N//4, K]  (qmodule.py:26-65)."""
-    q = np.asarray(q)
+    """q[N, K] integers  ->  int16 [N//4, K]  (qmodule.py:26-65).
+
+    The reference ORs the four shifted values of one int16 WITHOUT masking (:50-55) and
+    then wraps to int16 (:59): integers outside 0..15 corrupt the neighbouring nibbles.
+    Restated as is (values in 0..15 are the only ones the quantiser is meant to produce)."""
+    q = np.asarray(q).astype(np.int64)
     N, K = q.shape
     assert N % INTERLEAVE == 0 and K % KSTRIDE == 0
     nn, kk = np.meshgrid(np.arange(N), np.arange(K), indexing="ij")
     r, c, j = packed_index(nn, kk)
-    out = np.zeros((N // 4, K), dtype=np.uint16)
-    np.bitwise_or.at(out, (r, c), (q.astype(np.uint16) & 0xF) << (4 * j).astype(np.uint16))
-    return out.view(np.int16)
+    out = np.zeros((N // 4, K), dtype=np.int64)
+    np.bitwise_or.at(out, (r, c), q << (4 * j))
+    return out.astype(np.int16)
 
 
 def unpack_intweight(qweight: np.ndarray) -> np.ndarray:

@@ -84,6 +84,28 @@ def main():
         out[f"fl_{tag}_bias"] = f(wq.bias)
         assert tuple(wq.qweight.shape) == (N // 4, K) and wq.qweight.dtype == torch.int16
 
+    # 3b. out-of-range integers through pack_intweight (unmasked OR, qmodule.py:50-55) and from_linear on
+    #     RAW (not fake-quantised) weights, where round((w + s*z)/s) can leave 0..15 in half precision
+    q = torch.randint(-3, 19, (16, 128), generator=g, dtype=torch.int32)
+    out["packoob_q"] = q.numpy().astype(np.int32)
+    out["packoob_packed"] = qmodule.pack_intweight(q, interleave=4, kstride=64).numpy()
+    for tag, dt in (("f16", torch.float16), ("bf16", torch.bfloat16)):
+        N, K, G = 32, 256, 128
+        lin = torch.nn.Linear(K, N, bias=False)
+        with torch.no_grad():
+            lin.weight.copy_(torch.randn(N, K, generator=g) * 0.02)
+        lin = lin.to(dt)
+        _, scales, zeros = pseudo_quantize_tensor(
+            lin.weight.data.clone(), n_bit=4, zero_point=True, q_group_size=G, get_scale_zp=True)
+        wq = qmodule.WQLinear.from_linear(lin, 4, G, False, scales, zeros)
+        f = lambda t: t.detach().float().numpy()
+        out[f"flraw_{tag}_w"] = f(lin.weight.data)
+        out[f"flraw_{tag}_scales"] = f(scales)
+        out[f"flraw_{tag}_zeros"] = f(zeros)
+        out[f"flraw_{tag}_qweight"] = wq.qweight.numpy()
+        out[f"flraw_{tag}_sbuf"] = f(wq.scales)
+        out[f"flraw_{tag}_zbuf"] = f(wq.scaled_zeros)
+
     # 4. buffer shapes declared by WQLinear.__init__ for the BASELINE shapes
     shapes = []
     for (K, N) in [(4096, 4096), (4096, 6144), (4096, 14336), (14336, 4096), (8192, 1280),

@@ -113,3 +113,44 @@ def test_oracle_is_not_imported_by_the_product():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 assert "oracle" not in open(os.path.join(dirpath, f)).read().replace("test oracle", ""), f
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/awq"), reason="reference checkout only exists in the build container")
+def test_unmodified_reference_wqlinear_binds_to_this_engine():
+    """The reference's own qmodule.py does `import awq_inference_engine` (qmodule.py:4): with our plugin
+    directory on sys.path it must pick up THIS build, and its WQLinear.forward must reach our entry points
+    (which reject CPU tensors instead of computing on the host)."""
+    import importlib.util
+    import sys
+    P.install()
+    sys.modules.pop("awq_inference_engine", None)
+    spec = importlib.util.spec_from_file_location("ref_qmodule_live", "/root/reference/awq/quantize/qmodule.py")
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    assert os.path.abspath(ref.awq_inference_engine.__file__).startswith(P.install())
+    m = ref.WQLinear(4, 128, 256, 64, False, "cpu")
+    ours = P.WQLinear(4, 128, 256, 64, False, "cpu")
+    assert {k: (v.shape, v.dtype) for k, v in m.state_dict().items()} == \
+           {k: (v.shape, v.dtype) for k, v in ours.state_dict().items()}
+    for tokens in (1, 9):      # GEMV branch and GEMM branch of the reference's forward (qmodule.py:206-220)
+        with pytest.raises(RuntimeError, match="CUDA"):
+            m(torch.zeros(tokens, 256, dtype=torch.float16))
+
+
+def test_packer_out_of_range_and_raw_weight_from_linear_match_reference():
+    """Unmasked OR of out-of-range integers (reference qmodule.py:50-55) is reproduced bit for bit."""
+    q = torch.from_numpy(G["packoob_q"])
+    assert np.array_equal(P.pack_intweight(q).numpy(), G["packoob_packed"])
+    assert np.array_equal(O.pack_intweight(G["packoob_q"]), G["packoob_packed"])
+    for tag, dt in (("f16", torch.float16), ("bf16", torch.bfloat16)):
+        N, K = G[f"flraw_{tag}_w"].shape
+        lin = torch.nn.Linear(K, N, bias=False)
+        lin.weight.data = torch.from_numpy(G[f"flraw_{tag}_w"]).to(dt)
+        lin = lin.to(dt)
+        m = P.WQLinear.from_linear(lin, 4, 128, False, torch.from_numpy(G[f"flraw_{tag}_scales"]).to(dt),
+                                   torch.from_numpy(G[f"flraw_{tag}_zeros"]).to(dt))
+        assert np.array_equal(m.qweight.numpy(), G[f"flraw_{tag}_qweight"])
+        assert np.array_equal(m.scales.float().numpy(), G[f"flraw_{tag}_sbuf"])
+        assert np.array_equal(m.scaled_zeros.float().numpy(), G[f"flraw_{tag}_zbuf"])
+        qw, sbuf, zbuf = O.from_linear(G[f"flraw_{tag}_w"], G[f"flraw_{tag}_scales"], G[f"flraw_{tag}_zeros"], 128, tag)
+        assert np.array_equal(qw, G[f"flraw_{tag}_qweight"])

@@ -81,3 +81,25 @@ def test_forward_linearity_and_dispatch():
     e = np.zeros((1, K)); e[0, 77] = 1.0
     assert np.array_equal(O.wq_linear_forward(e, qw, s, z)[0], O.dequant_weight(qw, s, z)[:, 77])
     assert O.dispatch_is_gemv((1, 7, K)) and not O.dispatch_is_gemv((1, 8, K))
+
+
+def test_cpu_path_matches_numpy_oracle():
+    """oracle/cpu_path.py (the timed pure-PyTorch CPU arm) == numpy oracle up to the operand rounding."""
+    import torch
+    from oracle import cpu_path
+    rng = np.random.default_rng(3)
+    N, K = 64, 1408            # 11 groups -> 16 scale rows (padding rows present)
+    qw = rng.integers(-32768, 32767, (N // 4, K)).astype(np.int16)
+    rows = O.scale_rows(K)
+    s = np.zeros((rows, N), np.float16)
+    s[: K // 128] = (0.004 + 0.012 * rng.random((K // 128, N))).astype(np.float16)
+    z = (-s.astype(np.float32) * rng.integers(0, 16, s.shape)).astype(np.float16)
+    x = rng.standard_normal((3, K)).astype(np.float16)
+    tq, ts, tz, tx = (torch.from_numpy(a) for a in (qw, s, z, x))
+    assert np.array_equal(cpu_path.unpack_intweight(tq).numpy(), O.unpack_intweight(qw))
+    w_exact = O.unpack_intweight(qw).astype(np.float64) * np.repeat(s[: K // 128].T.astype(np.float64), 128, 1) \
+        + np.repeat(z[: K // 128].T.astype(np.float64), 128, 1)
+    assert np.allclose(cpu_path.dequant_weight(tq, ts, tz).double().numpy(), w_exact, rtol=1e-6, atol=1e-7)
+    y = cpu_path.wq_linear_forward(tx, tq, ts, tz).double().numpy()
+    y64 = O.wq_linear_forward(x, qw, s, z)
+    assert np.linalg.norm(y - y64) / np.linalg.norm(y64) < 1e-3   # fp16 operand rounding of the kernels' contract

@@ -44,6 +44,14 @@ def build_lib(force=False):
     return LIB
 
 
+def build_trace_lib():
+    """Debug variant with per-launch timestamps (scripts/trace_chain.py); not part of the product."""
+    out = os.path.join(HERE, "lib", "libb200awq_trace.so")
+    srcs = [os.path.join(CSRC, f) for f in ("api.cu", "w4a16_stream.cu", "w4a16_umma.cu")]
+    _run([os.environ.get("NVCC", "nvcc")] + NVCC_FLAGS + ["-DB200AWQ_TRACE", "-shared", "-o", out] + srcs)
+    return out
+
+
 def build_ext(force=False):
     src = os.path.join(CSRC, "torch_ext.cpp")
     if not force and _newer(EXT, [src, LIB, os.path.join(INCLUDE, "b200awq.h"), __file__]):
@@ -68,3 +76,5 @@ def build_all(force=False):
 
 if __name__ == "__main__":
     print(*build_all("--force" in sys.argv), sep="\n")
+    if "--trace" in sys.argv:
+        print(build_trace_lib())

@@ -50,8 +50,9 @@ int check_common(const void* x, const void* qw, const void* sc, const void* sz, 
 
 b200awq::StreamTuning stream_tuning() {
   b200awq::StreamTuning t;
-  t.mode = env_int("B200AWQ_STREAM_MODE", 0);
+  t.mode = env_int("B200AWQ_STREAM_MODE", -1);
   t.kc = env_int("B200AWQ_STREAM_KC", 0);
+  t.rpb = env_int("B200AWQ_STREAM_RPB", 0);
   return t;
 }
 b200awq::UmmaTuning umma_tuning() {

@@ -6,11 +6,16 @@
 //     is 2*RO contiguous byte ranges (the packing interleaves 4 rows, so a 4-row "quad"
 //     is contiguous over k); they are pulled into shared memory with bulk async copies
 //     (cp.async.bulk -> SASS UBLKCP) issued by ONE thread at the very top of the kernel,
-//     so all of the CTA's HBM traffic is in flight at once and no registers are pinned
-//     by outstanding loads.  Several CTAs co-reside per SM -> 100+ KB in flight per SM.
-//   * the weight prefetch is issued BEFORE griddepcontrol.wait: with programmatic
-//     dependent launch the next linear layer streams its weights while the previous
-//     one is still reducing / draining.  Activations are only touched after the wait.
+//     in k order and in pieces that each complete on their own mbarrier, so all of the
+//     CTA's HBM traffic is in flight at once, no registers are pinned by outstanding
+//     loads, and the math starts as soon as the first piece has landed.  Several CTAs
+//     co-reside per SM -> 100+ KB in flight per SM.
+//   * everything that does not depend on the activations -- the weight prefetch and the
+//     staging of this CTA's scales / zeros into shared memory -- happens BEFORE
+//     griddepcontrol.wait: with programmatic dependent launch the next linear layer
+//     streams its weights while the previous one is still computing / draining.  Only
+//     the part after the wait is serialised between consecutive layers, so it is kept
+//     short: one round trip to L2 for the activations, then math out of shared memory.
 //   * each lane dequantises its own 16-byte chunks (32 weights of ONE output channel,
 //     for two channels 8 apart) in registers and feeds them as the A operand of
 //     m16n8k16 tensor-core MACs (rows = 16 output channels, columns = 8 tokens).  The k
@@ -18,28 +23,74 @@
 //     lane-local k slots, so the reference's register-oriented packing needs no shuffles;
 //     the activations are re-ordered once while they are staged into shared memory so
 //     that every B fragment is one aligned register pair.  Accumulation is fp32.
-//   * the 4 warps of a CTA split the k groups; partials are reduced through shared
+//   * the 8 warps of a CTA split the k groups; partials are reduced through shared
 //     memory, and across the CTAs of a thread-block cluster (split-K for large k)
 //     through distributed shared memory.  No global atomics, no workspace.
 //
-// MODE 0 (default): operands w~ = rn_T(q*s + z) bit-identical to the reference's.
-// MODE 1: exact integer q as operand; scale/zero applied per 128-k group in fp32:
-//         y += s*(sum_k q_k x_k) + z*(sum_k x_k).
-// MODE 2: raw biased operands (1024+q | 1024+16q for fp16, 128+q for bf16) with the
-//         high-nibble activations pre-scaled by 1/16 (fp16); the bias is removed per group
-//         in fp32:  y += s*(acc - C) + z*X,  C = 1024*X_lo + 64*X_hi  (bf16: 128*X).
+// MODE 0: operands w~ = rn_T(q*s + z) bit-identical to the reference's (13 ALU ops per 8
+//         weights).  Default for bf16, where operand rounding (2^-9) is part of the 1e-3 contract.
+// MODE 2: raw biased operands straight out of the LOP3 (1024+q for low nibbles | 64+q for high
+//         nibbles in fp16, 128+q for bf16; 5 ALU ops per 8 weights); scale, zero and the bias are
+//         applied per 128-k group in fp32:
+//             y += s*(acc - C) + z*X,   X = sum_k x_k,  C = 1024*X_lo + 64*X_hi  (bf16: 128*X).
+//         Exact in the integer q; differs from MODE 0 only by not rounding q*s+z to T.
+//         Default for fp16 (that rounding is 2^-12 relative: ~2e-4 normwise, inside 1e-3).
 #include "w4_common.cuh"
 #include "w4a16_kernels.h"
 
 namespace b200awq {
 
-constexpr int kStreamThreads = 128;
-constexpr int kStreamWarps = 4;
+constexpr int kStreamThreads = 256;
+constexpr int kStreamWarps = 8;
+constexpr int kRoundK = kStreamWarps * kGroup;  // input channels consumed per round of the 4 warps
+
+#ifdef B200AWQ_TRACE
+// Debug build only (scripts/trace_chain.py): wall-clock stamps of the first and last CTA of each launch.
+__device__ unsigned long long g_trace_buf[1024 * 2 * 8];
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define B200AWQ_STAMP(ev)                                                     \
+  if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) \
+  g_trace_buf[(((unsigned)seq & 1023u) * 2 + (blockIdx.x != 0)) * 8 + (ev)] = globaltimer_ns()
+#else
+#define B200AWQ_STAMP(ev)
+#endif
+
+struct StreamSmem {
+  int w, s, z, x, red, cpart, xsum, bars, total;
+};
+
+__host__ __device__ inline StreamSmem stream_smem_layout(int RO, int TT, int MODE, int M, int Kc, int rpb) {
+  StreamSmem L;
+  const int ng = Kc / kGroup;
+  const int nbar = ((ng + kStreamWarps - 1) / kStreamWarps + rpb - 1) / rpb;
+  int off = 0;
+  L.w = off, off += 2 * RO * Kc * 2;
+  L.s = off, off += ng * 8 * RO * 2;
+  L.z = off, off += ng * 8 * RO * 2;
+  off = (off + 15) & ~15;
+  L.x = off, off += M * (Kc * 2 + 16);
+  L.red = off, off += kStreamWarps * TT * 128 * 4;
+  L.cpart = off, off += TT * 128 * 4;
+  L.xsum = off, off += (MODE ? 8 * TT * ng * 8 : 0);
+  L.bars = off, off += (nbar + 1) * 8;
+  L.total = off;
+  return L;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 template <typename T, int RO, int TT, int MODE>
-__global__ void __launch_bounds__(kStreamThreads)
+__global__ void __launch_bounds__(kStreamThreads, TT == 1 ? 3 : 2)
 w4a16_stream_kernel(const T* __restrict__ x, const uint16_t* __restrict__ qw, const T* __restrict__ scales,
-                    const T* __restrict__ szeros, T* __restrict__ y, int M, int N, int K, int Kc, int S) {
+                    const T* __restrict__ szeros, T* __restrict__ y, int M, int N, int K, int Kc, int S, int rpb, int seq) {
+  B200AWQ_STAMP(0);
   constexpr bool kBf16 = TypeTraits<T>::kIsBf16;
   constexpr int R = 8 * RO;  // output channels per CTA
   extern __shared__ __align__(128) uint8_t smem[];
@@ -50,100 +101,110 @@ w4a16_stream_kernel(const T* __restrict__ x, const uint16_t* __restrict__ qw, co
   const int n0 = rb * R;
   const int kbase = rank * Kc;
   const int ngroups = Kc / kGroup;
+  const int nrounds = (ngroups + kStreamWarps - 1) / kStreamWarps;
+  const int nbar = (nrounds + rpb - 1) / rpb;
   const int wrow = Kc * 2;       // bytes of one 4-row quad over this CTA's k range
   const int xrow = Kc * 2 + 16;  // padded activation row (bank spread between tokens)
+  const StreamSmem L = stream_smem_layout(RO, TT, MODE, M, Kc, rpb);
 
-  uint8_t* wbuf = smem;
-  uint8_t* xbuf = wbuf + 2 * RO * wrow;
-  float* red = reinterpret_cast<float*>(xbuf + M * xrow);  // [warp][tt][16 rows][8 tok]
-  float* cpart = red + kStreamWarps * TT * 128;            // [tt][16][8]
-  float2* xsum = reinterpret_cast<float2*>(cpart + TT * 128);  // [8 TT tok][group] {X, C}   (MODE >= 1)
-  uint8_t* zblk = reinterpret_cast<uint8_t*>(xsum + (MODE ? 8 * TT * ngroups : 0));  // 64 zero bytes
-  uint64_t* bars = reinterpret_cast<uint64_t*>(zblk + 64);
+  uint8_t* wbuf = smem + L.w;
+  uint16_t* sbuf = reinterpret_cast<uint16_t*>(smem + L.s);  // [group][R]
+  uint16_t* zbuf = reinterpret_cast<uint16_t*>(smem + L.z);
+  uint8_t* xbuf = smem + L.x;                                // [token][Kc] natural order (+16 B pad per row)
+  float* red = reinterpret_cast<float*>(smem + L.red);      // [warp][tt][16 rows][8 tok]
+  float* cpart = reinterpret_cast<float*>(smem + L.cpart);  // [tt][16][8]
+  float2* xsum = reinterpret_cast<float2*>(smem + L.xsum);  // [8 TT tok][group] {X, C}   (MODE 2)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
+  uint64_t* xbar = bars + nbar;
 
+  // ---- weight prefetch: 2*RO quad rows x nbar pieces of (rpb * 1024 k = 2 rpb KB), k-major issue order
   if (tid == 0) {
-    mbar_init(&bars[0], 1);
+    for (int b = 0; b <= nbar; ++b) mbar_init(&bars[b], 1);
     mbar_fence_init();
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    mbar_expect_tx(&bars[0], 2 * RO * wrow);
+    const int piece = rpb * kRoundK * 2;  // bytes per quad row per barrier
+    for (int b = 0; b < nbar; ++b) {
+      const int off = b * piece;
+      const int len = min(piece, wrow - off);
+      mbar_expect_tx(&bars[b], 2 * RO * len);
 #pragma unroll
-    for (int qd = 0; qd < 2 * RO; ++qd)
-      bulk_g2s(wbuf + qd * wrow, qw + (size_t)(rb * 2 * RO + qd) * K + kbase, wrow, &bars[0]);
-  }
-  {
-    float* xz = reinterpret_cast<float*>(xsum);  // xsum (if any) and the zero block are contiguous
-    for (int i = tid; i < (MODE ? 16 * TT * ngroups : 0) + 16; i += kStreamThreads) xz[i] = 0.f;
-  }
-
-  // scale / zero of this lane's output channels (row g of each octet), one 16-bit value each
-  const uint16_t* sp = reinterpret_cast<const uint16_t*>(scales) + (size_t)(kbase / kGroup) * N + n0 + g;
-  const uint16_t* zp = reinterpret_cast<const uint16_t*>(szeros) + (size_t)(kbase / kGroup) * N + n0 + g;
-  uint32_t s_cur[RO], z_cur[RO];
-#pragma unroll
-  for (int ro = 0; ro < RO; ++ro) {
-    s_cur[ro] = 0;
-    z_cur[ro] = 0;
-  }
-  sp += (size_t)warp * N;
-  zp += (size_t)warp * N;
-  const size_t sstep = (size_t)kStreamWarps * N;
-  if (warp < ngroups) {
-#pragma unroll
-    for (int ro = 0; ro < RO; ++ro) {
-      s_cur[ro] = __ldg(sp + 8 * ro);
-      z_cur[ro] = __ldg(zp + 8 * ro);
+      for (int qd = 0; qd < 2 * RO; ++qd)
+        bulk_g2s(wbuf + qd * wrow + off, reinterpret_cast<const uint8_t*>(qw + (size_t)(rb * 2 * RO + qd) * K + kbase) + off,
+                 len, &bars[b]);
     }
   }
-
   pdl_launch_dependents();
-  __syncthreads();        // barrier init + xsum zeroing visible
-  pdl_wait_prior_grid();  // activations (and y) belong to the stream order from here on
-
-  // ---- stage activations: x[m, kbase + ...] -> xbuf, re-ordered per 16-element chunk
-  //      (pairs p0..p7) -> (p0,p4,p1,p5 | p2,p6,p3,p7) so that the pair of B registers of one
-  //      MMA is one aligned 8-byte piece; MODE 2/fp16 also scales the upper half by 1/16.
+  B200AWQ_STAMP(1);
+  // ---- scales / zeros of this CTA's rows and groups -> shared memory, asynchronously (16-byte pieces)
   {
-    const int chunks = Kc / 16;
-    for (int idx = tid; idx < M * chunks; idx += kStreamThreads) {
-      const int m = idx / chunks, c = idx - m * chunks;
-      const uint4* src = reinterpret_cast<const uint4*>(x + (size_t)m * K + kbase + c * 16);
-      uint4 a = __ldg(src), b = __ldg(src + 1);
-      if (MODE) {
+    constexpr int PPG = R / 8;  // 16-byte pieces per group per tensor
+    const int pieces = ngroups * PPG;
+    const uint8_t* sg = reinterpret_cast<const uint8_t*>(scales) + ((size_t)(kbase / kGroup) * N + n0) * 2;
+    const uint8_t* zg = reinterpret_cast<const uint8_t*>(szeros) + ((size_t)(kbase / kGroup) * N + n0) * 2;
+    for (int i = tid; i < 2 * pieces; i += kStreamThreads) {
+      const int which = i >= pieces;
+      const int j = which ? i - pieces : i;
+      const int grp = j / PPG, pc = j - grp * PPG;
+      cp_async16(reinterpret_cast<uint8_t*>(which ? zbuf : sbuf) + (grp * PPG + pc) * 16,
+                 (which ? zg : sg) + (size_t)grp * N * 2 + pc * 16);
+    }
+    if (MODE) {  // tokens M .. 8*TT-1 do not exist: their correction terms must read as zero
+      for (int i = tid + M * ngroups; i < 8 * TT * ngroups; i += kStreamThreads) xsum[i] = make_float2(0.f, 0.f);
+    }
+    cp_async_wait_all();
+  }
+  __syncthreads();  // barrier inits, scales / zeros and the zeroed correction terms visible to everyone
+  B200AWQ_STAMP(2);
+  pdl_wait_prior_grid();  // activations (and y) belong to the stream order from here on
+  B200AWQ_STAMP(3);
+
+  // ---- activations: M bulk copies x[m, kbase .. kbase + Kc) -> xbuf (natural order)
+  if (tid == 0) {
+    mbar_expect_tx(xbar, (uint32_t)M * Kc * 2);
+    for (int m = 0; m < M; ++m) bulk_g2s(xbuf + m * xrow, x + (size_t)m * K + kbase, Kc * 2, xbar);
+  }
+  mbar_wait(xbar, 0);
+  if (MODE) {
+    // {X, C} of (token, group) for THIS warp's groups only (nobody else reads them): lane = (group
+    // slot, 16-element chunk); the first 16 B of a chunk sit on low-nibble positions, the second on
+    // high-nibble ones (pairs 0-3 | 4-7 of each half of the 32-k block).
+    const int gslot = lane >> 3, chunk = lane & 7;
+    for (int g0 = warp; g0 < ngroups; g0 += 4 * kStreamWarps) {  // 4 of this warp's groups per pass
+      const int G = g0 + gslot * kStreamWarps;
+      for (int m = 0; m < M; ++m) {
         float lo = 0.f, hi = 0.f;
-        const uint32_t av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+        if (G < ngroups) {
+          const uint4* src = reinterpret_cast<const uint4*>(xbuf + m * xrow + G * 256 + chunk * 32);
+          const uint4 va = src[0], vb = src[1];
+          const uint32_t av[4] = {va.x, va.y, va.z, va.w}, bv[4] = {vb.x, vb.y, vb.z, vb.w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float2 fa, fb;
-          if constexpr (kBf16) {
-            fa = __bfloat1622float2(u32_as_b2(av[i]));
-            fb = __bfloat1622float2(u32_as_b2(bv[i]));
-          } else {
-            fa = __half22float2(u32_as_h2(av[i]));
-            fb = __half22float2(u32_as_h2(bv[i]));
+          for (int e = 0; e < 4; ++e) {
+            float2 fa, fb;
+            if constexpr (kBf16) {
+              fa = __bfloat1622float2(u32_as_b2(av[e]));
+              fb = __bfloat1622float2(u32_as_b2(bv[e]));
+            } else {
+              fa = __half22float2(u32_as_h2(av[e]));
+              fb = __half22float2(u32_as_h2(bv[e]));
+            }
+            lo += fa.x + fa.y;
+            hi += fb.x + fb.y;
           }
-          lo += fa.x + fa.y;
-          hi += fb.x + fb.y;
         }
-        float X = lo + hi, C = 0.f;
-        if (MODE == 2) C = kBf16 ? 128.f * X : 1024.f * lo + 64.f * hi;
-        float* dst = reinterpret_cast<float*>(&xsum[m * ngroups + (c >> 3)]);
-        atomicAdd(dst, X);
-        if (MODE == 2) atomicAdd(dst + 1, C);
-        if (MODE == 2 && !kBf16) {
-          const __half2 k16th = u32_as_h2(0x2c002c00u);
-          b.x = h2_as_u32(__hmul2(u32_as_h2(b.x), k16th));
-          b.y = h2_as_u32(__hmul2(u32_as_h2(b.y), k16th));
-          b.z = h2_as_u32(__hmul2(u32_as_h2(b.z), k16th));
-          b.w = h2_as_u32(__hmul2(u32_as_h2(b.w), k16th));
+#pragma unroll
+        for (int d = 1; d < 8; d <<= 1) {
+          lo += __shfl_xor_sync(0xffffffffu, lo, d);
+          hi += __shfl_xor_sync(0xffffffffu, hi, d);
+        }
+        if (chunk == 0 && G < ngroups) {
+          const float X = lo + hi;
+          xsum[m * ngroups + G] = make_float2(X, kBf16 ? 128.f * X : 1024.f * lo + 64.f * hi);
         }
       }
-      uint4* dst = reinterpret_cast<uint4*>(xbuf + m * xrow + c * 32);
-      dst[0] = make_uint4(a.x, b.x, a.y, b.y);
-      dst[1] = make_uint4(a.z, b.z, a.w, b.w);
     }
+    __syncwarp();
   }
-  __syncthreads();
-  mbar_wait(&bars[0], 0);
+  B200AWQ_STAMP(4);
 
   float acc[TT][4];
 #pragma unroll
@@ -152,44 +213,41 @@ w4a16_stream_kernel(const T* __restrict__ x, const uint16_t* __restrict__ qw, co
     for (int i = 0; i < 4; ++i) acc[t][i] = 0.f;
   const float zero4[4] = {0.f, 0.f, 0.f, 0.f};
 
-  // per-lane walking pointers (lanes whose token does not exist read the zero block forever)
+  // per-lane walking pointers; lanes whose token does not exist feed zeros
   const uint8_t* xp[TT];
-  int xstep[TT];
-  const float2* sump[TT][2];
+  bool live[TT];
 #pragma unroll
   for (int t = 0; t < TT; ++t) {
     const int tok = g + 8 * t;
-    const bool live = tok < M;
-    xp[t] = live ? xbuf + tok * xrow + (warp * kGroup + tig * 32) * 2 : zblk;
-    xstep[t] = live ? kStreamWarps * kGroup * 2 : 0;
-    sump[t][0] = xsum + (8 * t + 2 * tig) * ngroups + warp;
-    sump[t][1] = sump[t][0] + ngroups;
+    live[t] = tok < M;
+    xp[t] = xbuf + (live[t] ? tok : 0) * xrow + (warp * kGroup + tig * 32) * 2;
   }
   const uint8_t* wp = wbuf + (g >> 2) * wrow + (warp * 2 + (tig >> 1)) * 128 + (g & 3) * 32 + (tig & 1) * 16;
+  const uint16_t* sq = sbuf + warp * R + g;
+  const uint16_t* zq = zbuf + warp * R + g;
+  const float2* sump = xsum + (2 * tig) * ngroups + warp;  // token 2 tig (+ 8 t), this warp's first group
+  uint4 xq[TT][4];
+#pragma unroll
+  for (int t = 0; t < TT; ++t)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) xq[t][j] = make_uint4(0, 0, 0, 0);
 
-  for (int G = warp; G < ngroups; G += kStreamWarps) {
-    uint32_t s_nxt[RO], z_nxt[RO];
-#pragma unroll
-    for (int ro = 0; ro < RO; ++ro) {
-      s_nxt[ro] = 0;
-      z_nxt[ro] = 0;
+  for (int rnd = 0, G = warp, left = 0, bar = 0; rnd < nrounds; ++rnd, G += kStreamWarps) {
+    if (left == 0) {
+      mbar_wait(&bars[bar++], 0);
+      left = rpb;
     }
-    sp += sstep;
-    zp += sstep;
-    if (G + kStreamWarps < ngroups) {
-#pragma unroll
-      for (int ro = 0; ro < RO; ++ro) {
-        s_nxt[ro] = __ldg(sp + 8 * ro);
-        z_nxt[ro] = __ldg(zp + 8 * ro);
-      }
-    }
-    // B fragments: token g (+ 8 t) of this lane, the 32 k of block (G, tig), staged order
-    uint4 xq[TT][4];
+    --left;
+    if (G >= ngroups) break;  // only in the last round, when ngroups % 8 != 0
+    // B fragments: token g (+ 8 t) of this lane, the 32 k of block (G, tig) in natural order: xq[j]
+    // holds the k pairs 4j .. 4j+3 = what nibble pair j of words 0..3 multiplies (dead lanes keep 0)
 #pragma unroll
     for (int t = 0; t < TT; ++t) {
+      if (live[t]) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) xq[t][i] = reinterpret_cast<const uint4*>(xp[t])[i];
-      xp[t] += xstep[t];
+        for (int j = 0; j < 4; ++j) xq[t][j] = reinterpret_cast<const uint4*>(xp[t])[j];
+      }
+      xp[t] += kRoundK * 2;
     }
     // A: the 16-byte chunk of (row n0 + 8 ro + g, 32-k block 4G + tig) for ro = 0 (rows 0-7 of
     // the MMA) and ro = 1 (rows 8-15)
@@ -203,70 +261,67 @@ w4a16_stream_kernel(const T* __restrict__ x, const uint16_t* __restrict__ qw, co
       }
       wp += kStreamWarps * 256;
     }
-    const uint32_t sa2 = s_cur[0] * 0x00010001u, za2 = z_cur[0] * 0x00010001u;
-    const uint32_t sb2 = s_cur[RO - 1] * 0x00010001u, zb2 = z_cur[RO - 1] * 0x00010001u;
+    const uint16_t s_a = sq[0], z_a = zq[0], s_b = sq[8 * (RO - 1)], z_b = zq[8 * (RO - 1)];
+    sq += kStreamWarps * R;
+    zq += kStreamWarps * R;
+    const uint32_t sa2 = splat16(s_a), za2 = splat16(z_a), sb2 = splat16(s_b), zb2 = splat16(z_b);
 
-    float part[TT][4];
+    float part[TT][4], part2[TT][4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      uint32_t oa[4], ob[4] = {0, 0, 0, 0};
+    for (int uu = 0; uu < 4; uu += 2) {
+      // words uu, uu+1 of both octets; the MMA of nibble pair j takes (word uu, word uu+1) as its two
+      // k slots, so its B operand is the ADJACENT register pair (4j + uu, 4j + uu + 1) of xq[j]
+      uint32_t oa0[4], oa1[4], ob0[4] = {0, 0, 0, 0}, ob1[4] = {0, 0, 0, 0};
       if (MODE == 0) {
-        dequant_word<T>(wa[u], sa2, za2, oa);
-        if (RO == 2) dequant_word<T>(wb[u], sb2, zb2, ob);
-      } else if (MODE == 1) {
-        unpack_word<T>(wa[u], oa);
-        if (RO == 2) unpack_word<T>(wb[u], ob);
+        dequant_word<T>(wa[uu], sa2, za2, oa0);
+        dequant_word<T>(wa[uu + 1], sa2, za2, oa1);
+        if (RO == 2) {
+          dequant_word<T>(wb[uu], sb2, zb2, ob0);
+          dequant_word<T>(wb[uu + 1], sb2, zb2, ob1);
+        }
       } else {
-        unpack_word_biased<T>(wa[u], oa);
-        if (RO == 2) unpack_word_biased<T>(wb[u], ob);
+        unpack_word_biased<T>(wa[uu], oa0);
+        unpack_word_biased<T>(wa[uu + 1], oa1);
+        if (RO == 2) {
+          unpack_word_biased<T>(wb[uu], ob0);
+          unpack_word_biased<T>(wb[uu + 1], ob1);
+        }
       }
 #pragma unroll
       for (int t = 0; t < TT; ++t) {
-        // staged order: xq[0] = (p0,p4,p1,p5), xq[1] = (p2,p6,p3,p7), xq[2..3] the same + 8
-        const uint4 lo = xq[t][u >> 1], hi = xq[t][2 + (u >> 1)];
-        const uint32_t b00 = (u & 1) ? lo.z : lo.x, b01 = (u & 1) ? lo.w : lo.y;
-        const uint32_t b10 = (u & 1) ? hi.z : hi.x, b11 = (u & 1) ? hi.w : hi.y;
-        if (MODE == 0) {
-          mma_16816<T>(acc[t], oa[0], ob[0], oa[1], ob[1], b00, b01, acc[t]);
-          mma_16816<T>(acc[t], oa[2], ob[2], oa[3], ob[3], b10, b11, acc[t]);
-        } else {
-          if (u == 0)
-            mma_16816<T>(part[t], oa[0], ob[0], oa[1], ob[1], b00, b01, zero4);
-          else
-            mma_16816<T>(part[t], oa[0], ob[0], oa[1], ob[1], b00, b01, part[t]);
-          mma_16816<T>(part[t], oa[2], ob[2], oa[3], ob[3], b10, b11, part[t]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t b0 = uu ? xq[t][j].z : xq[t][j].x, b1 = uu ? xq[t][j].w : xq[t][j].y;
+          if (MODE == 0) {
+            mma_16816<T>(acc[t], oa0[j], ob0[j], oa1[j], ob1[j], b0, b1, acc[t]);
+          } else {
+            // two independent accumulation chains (even / odd j); low-nibble pairs are j = 0, 2
+            float(&dst)[4] = (j & 1) ? part2[t] : part[t];
+            if (uu == 0 && j < 2)
+              mma_16816<T>(dst, oa0[j], ob0[j], oa1[j], ob1[j], b0, b1, zero4);
+            else
+              mma_16816<T>(dst, oa0[j], ob0[j], oa1[j], ob1[j], b0, b1, dst);
+          }
         }
       }
     }
     if (MODE) {
-      // part[t][0..1]: (row g of octet 0, tokens 2tig, 2tig+1); part[t][2..3]: row g of octet 1
-      const float sa = bits16_to_float((uint16_t)s_cur[0], kBf16), za = bits16_to_float((uint16_t)z_cur[0], kBf16);
-      const float sb = bits16_to_float((uint16_t)s_cur[RO - 1], kBf16), zb = bits16_to_float((uint16_t)z_cur[RO - 1], kBf16);
+      // part[t][0..1]: (row g of octet 0, tokens 8t + 2tig, + 1); part[t][2..3]: row g of octet 1
+      const float sa = bits16_to_float(s_a, kBf16), za = bits16_to_float(z_a, kBf16);
+      const float sb = bits16_to_float(s_b, kBf16), zb = bits16_to_float(z_b, kBf16);
 #pragma unroll
       for (int t = 0; t < TT; ++t) {
-        const float2 x0 = *sump[t][0], x1 = *sump[t][1];  // {X, C} of tokens 8t + 2tig, + 1 (zeros if absent)
-        sump[t][0] += kStreamWarps;
-        sump[t][1] += kStreamWarps;
-        if (MODE == 2) {
-          acc[t][0] += sa * (part[t][0] - x0.y) + za * x0.x;
-          acc[t][1] += sa * (part[t][1] - x1.y) + za * x1.x;
-          acc[t][2] += sb * (part[t][2] - x0.y) + zb * x0.x;
-          acc[t][3] += sb * (part[t][3] - x1.y) + zb * x1.x;
-        } else {
-          acc[t][0] += sa * part[t][0] + za * x0.x;
-          acc[t][1] += sa * part[t][1] + za * x1.x;
-          acc[t][2] += sb * part[t][2] + zb * x0.x;
-          acc[t][3] += sb * part[t][3] + zb * x1.x;
-        }
+        const float2 c0 = sump[(8 * t) * ngroups], c1 = sump[(8 * t + 1) * ngroups];  // {X, C}, zeros if absent
+        acc[t][0] = fmaf(za, c0.x, fmaf(sa, (part[t][0] - c0.y) + part2[t][0], acc[t][0]));
+        acc[t][1] = fmaf(za, c1.x, fmaf(sa, (part[t][1] - c1.y) + part2[t][1], acc[t][1]));
+        acc[t][2] = fmaf(zb, c0.x, fmaf(sb, (part[t][2] - c0.y) + part2[t][2], acc[t][2]));
+        acc[t][3] = fmaf(zb, c1.x, fmaf(sb, (part[t][3] - c1.y) + part2[t][3], acc[t][3]));
       }
-    }
-#pragma unroll
-    for (int ro = 0; ro < RO; ++ro) {
-      s_cur[ro] = s_nxt[ro];
-      z_cur[ro] = z_nxt[ro];
+      sump += kStreamWarps;
     }
   }
 
+  B200AWQ_STAMP(5);
   // acc[t][0..1]: (channel g, tokens 8t + 2tig, +1); acc[t][2..3]: channel 8 + g
 #pragma unroll
   for (int t = 0; t < TT; ++t) {
@@ -301,9 +356,23 @@ w4a16_stream_kernel(const T* __restrict__ x, const uint16_t* __restrict__ qw, co
     }
     cluster_sync_all();  // keep every CTA's shared memory alive until the leader has read it
   }
+  B200AWQ_STAMP(6);
 }
 
+#ifdef B200AWQ_TRACE
+extern "C" int b200awq_debug_read_trace(unsigned long long* host, int count) {
+  return (int)cudaMemcpyFromSymbol(host, g_trace_buf, sizeof(unsigned long long) * (size_t)count);
+}
+#endif
+
 // ------------------------------------------------------------------------------------ host
+constexpr int kStreamSmemCap = 200 * 1024;
+
+static int next_seq() {
+  static int seq = 0;
+  return seq++;
+}
+
 static int pick_splits(int K, int kc_target, int kc_env) {
   const int groups = K / kGroup;
   if (kc_env > 0 && kc_env % kGroup == 0 && K % kc_env == 0) {
@@ -321,22 +390,21 @@ static int pick_splits(int K, int kc_target, int kc_env) {
 
 template <typename T, int RO, int TT, int MODE>
 static int launch_stream_t(const void* x, const void* qw, const void* sc, const void* sz, void* y, int M, int N, int K,
-                           int S, bool pdl, cudaStream_t stream) {
+                           int S, int rpb, bool pdl, cudaStream_t stream) {
   const int Kc = K / S;
-  const size_t smem = (size_t)2 * RO * Kc * 2 + (size_t)M * (Kc * 2 + 16) + (size_t)(kStreamWarps + 1) * TT * 128 * 4 +
-                      (MODE ? (size_t)8 * TT * (Kc / kGroup) * 8 : 0) + 64 + 16;
-  if (smem > 200 * 1024) return B200AWQ_ERR_SHAPE;
+  const StreamSmem L = stream_smem_layout(RO, TT, MODE, M, Kc, rpb);
+  if (L.total > kStreamSmemCap) return B200AWQ_ERR_SHAPE;
   auto kern = w4a16_stream_kernel<T, RO, TT, MODE>;
   static bool attr_set = false;  // per instantiation
-  if (smem > 48 * 1024 && !attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (L.total > 48 * 1024 && !attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemCap);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(N / (8 * RO)) * S);
   cfg.blockDim = dim3(kStreamThreads);
-  cfg.dynamicSmemBytes = smem;
+  cfg.dynamicSmemBytes = L.total;
   cfg.stream = stream;
   cudaLaunchAttribute attrs[2];
   int na = 0;
@@ -355,19 +423,19 @@ static int launch_stream_t(const void* x, const void* qw, const void* sc, const 
   cfg.attrs = attrs;
   cfg.numAttrs = na;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, (const T*)x, (const uint16_t*)qw, (const T*)sc, (const T*)sz, (T*)y, M, N,
-                                     K, Kc, S);
+                                     K, Kc, S, rpb, next_seq());
   return e == cudaSuccess ? 0 : (int)e;
 }
 
 template <typename T, int MODE>
 static int launch_stream_m(const void* x, const void* qw, const void* sc, const void* sz, void* y, int M, int N, int K,
-                           int S, int ro, bool pdl, cudaStream_t stream) {
+                           int S, int ro, int rpb, bool pdl, cudaStream_t stream) {
   if (M <= 8) {
-    if (ro == 2) return launch_stream_t<T, 2, 1, MODE>(x, qw, sc, sz, y, M, N, K, S, pdl, stream);
-    return launch_stream_t<T, 1, 1, MODE>(x, qw, sc, sz, y, M, N, K, S, pdl, stream);
+    if (ro == 2) return launch_stream_t<T, 2, 1, MODE>(x, qw, sc, sz, y, M, N, K, S, rpb, pdl, stream);
+    return launch_stream_t<T, 1, 1, MODE>(x, qw, sc, sz, y, M, N, K, S, rpb, pdl, stream);
   }
-  if (ro == 2) return launch_stream_t<T, 2, 2, MODE>(x, qw, sc, sz, y, M, N, K, S, pdl, stream);
-  return launch_stream_t<T, 1, 2, MODE>(x, qw, sc, sz, y, M, N, K, S, pdl, stream);
+  if (ro == 2) return launch_stream_t<T, 2, 2, MODE>(x, qw, sc, sz, y, M, N, K, S, rpb, pdl, stream);
+  return launch_stream_t<T, 1, 2, MODE>(x, qw, sc, sz, y, M, N, K, S, rpb, pdl, stream);
 }
 
 int launch_stream(const void* x, const void* qw, const void* sc, const void* sz, void* y, int M, int N, int K, int dtype,
@@ -376,15 +444,15 @@ int launch_stream(const void* x, const void* qw, const void* sc, const void* sz,
   const int ro = (N % 16 == 0) ? 2 : 1;
   const int kc_target = M <= 2 ? 4096 : (M <= 8 ? 2048 : 1024);
   const int S = pick_splits(K, kc_target, tune.kc);
-  const int mode = (tune.mode >= 0 && tune.mode <= 2) ? tune.mode : 0;
+  const int rpb = tune.rpb > 0 ? tune.rpb : 1;
+  // default arithmetic: fp16 -> group-factored (MODE 2), bf16 -> operand-exact (MODE 0); see the header comment
+  const int mode = (tune.mode == 0 || tune.mode == 2) ? tune.mode : (dtype == B200AWQ_DTYPE_F16 ? 2 : 0);
   if (dtype == B200AWQ_DTYPE_F16) {
-    if (mode == 0) return launch_stream_m<__half, 0>(x, qw, sc, sz, y, M, N, K, S, ro, pdl, stream);
-    if (mode == 1) return launch_stream_m<__half, 1>(x, qw, sc, sz, y, M, N, K, S, ro, pdl, stream);
-    return launch_stream_m<__half, 2>(x, qw, sc, sz, y, M, N, K, S, ro, pdl, stream);
+    if (mode == 0) return launch_stream_m<__half, 0>(x, qw, sc, sz, y, M, N, K, S, ro, rpb, pdl, stream);
+    return launch_stream_m<__half, 2>(x, qw, sc, sz, y, M, N, K, S, ro, rpb, pdl, stream);
   }
-  if (mode == 0) return launch_stream_m<__nv_bfloat16, 0>(x, qw, sc, sz, y, M, N, K, S, ro, pdl, stream);
-  if (mode == 1) return launch_stream_m<__nv_bfloat16, 1>(x, qw, sc, sz, y, M, N, K, S, ro, pdl, stream);
-  return launch_stream_m<__nv_bfloat16, 2>(x, qw, sc, sz, y, M, N, K, S, ro, pdl, stream);
+  if (mode == 0) return launch_stream_m<__nv_bfloat16, 0>(x, qw, sc, sz, y, M, N, K, S, ro, rpb, pdl, stream);
+  return launch_stream_m<__nv_bfloat16, 2>(x, qw, sc, sz, y, M, N, K, S, ro, rpb, pdl, stream);
 }
 
 }  // namespace b200awq

@@ -1,0 +1,106 @@
+"""Tensor-parallel sharding of a WQLinear in PACKED space + the one all-reduce.
+
+The reference has no tensor parallelism (only accelerate layer placement, awq/utils/parallel.py);
+this is the new work BASELINE.json's north_star asks for: column-parallel qkv / gate / up,
+row-parallel o / down, and a single sum all-reduce on the row-parallel output.
+
+Why slicing the packed tensors is legal (closed form of pack_intweight, qmodule.py:26-65):
+  * the packing interleaves 4 output channels and is local to 64-k tiles, so
+    - a column-parallel (output-channel) shard is a contiguous block of ROWS of `qweight`
+      (granularity 4 channels; we require 8, the GEMV envelope) and of COLUMNS of scales/zeros;
+    - a row-parallel (input-channel) shard is a contiguous block of int16 COLUMNS of `qweight`
+      at 64-granularity; scales/zeros rows follow at group (128) granularity and are re-padded
+      to a multiple of 8 rows like calculate_zeros_width does (qmodule.py:11-23).
+One process per GPU; the collective is torch.distributed (NCCL over NVLink on the GPU box, gloo in
+the CPU tests).  The local product is always the sm_100a kernel: there is no CPU fallback.
+"""
+import torch
+import torch.nn as nn
+
+from .qmodule import WQLinear, calculate_zeros_width
+
+
+def _check_div(value, parts, gran, what):
+    if value % parts or (value // parts) % gran:
+        raise ValueError(f"{what}={value} cannot be split {parts} ways at granularity {gran}")
+    return value // parts
+
+
+def shard_column(qweight, scales, scaled_zeros, bias, rank, world, gran=8):
+    """Output-channel shard `rank` of `world`: rows of qweight, columns of scales / zeros / bias."""
+    N = qweight.shape[0] * 4
+    n = _check_div(N, world, gran, "out_features")
+    lo = rank * n
+    return (qweight[lo // 4:(lo + n) // 4].contiguous(), scales[:, lo:lo + n].contiguous(),
+            scaled_zeros[:, lo:lo + n].contiguous(), None if bias is None else bias[lo:lo + n].contiguous())
+
+
+def shard_row(qweight, scales, scaled_zeros, rank, world, group_size=128):
+    """Input-channel shard `rank` of `world`: int16 columns of qweight, group rows of scales / zeros
+    (re-padded to a multiple of 8 rows)."""
+    K = qweight.shape[1]
+    k = _check_div(K, world, max(group_size, 64), "in_features")
+    lo = rank * k
+    g0, ng = lo // group_size, k // group_size
+    rows = calculate_zeros_width(k, group_size) * 8
+    s = scales.new_zeros(rows, scales.shape[1])
+    z = scaled_zeros.new_zeros(rows, scaled_zeros.shape[1])
+    s[:ng] = scales[g0:g0 + ng]
+    z[:ng] = scaled_zeros[g0:g0 + ng]
+    return qweight[:, lo:lo + k].contiguous(), s, z
+
+
+def shard_fused_qkv(qweight, scales, scaled_zeros, bias, q_out, kv_out, rank, world):
+    """Fused [q; k; v] (tinychat/modules/fused_attn.py:566-594 concatenates along out_features):
+    shard q, k and v separately by head block, then re-concatenate per rank."""
+    parts, lo = [], 0
+    for n in (q_out, kv_out, kv_out):
+        sl = slice(lo, lo + n)
+        parts.append(shard_column(qweight[lo // 4:(lo + n) // 4], scales[:, sl], scaled_zeros[:, sl],
+                                  None if bias is None else bias[sl], rank, world))
+        lo += n
+    cat = lambda i, dim: torch.cat([p[i] for p in parts], dim=dim).contiguous()
+    return cat(0, 0), cat(1, 1), cat(2, 1), None if bias is None else cat(3, 0)
+
+
+def _from_tensors(qweight, scales, scaled_zeros, bias, group_size):
+    N, K = qweight.shape[0] * 4, qweight.shape[1]
+    m = WQLinear(4, group_size, K, N, bias is not None, qweight.device, dtype=scales.dtype)
+    m.qweight, m.scales, m.scaled_zeros = qweight, scales, scaled_zeros
+    if bias is not None:
+        m.bias = bias
+    return m
+
+
+class ColumnParallelWQLinear(nn.Module):
+    """y_local = x @ W[rows of this rank]^T.  Input replicated, output sharded; no communication."""
+
+    def __init__(self, full: WQLinear, rank, world, qkv_split=None):
+        super().__init__()
+        if qkv_split is None:
+            t = shard_column(full.qweight, full.scales, full.scaled_zeros, full.bias, rank, world)
+        else:
+            t = shard_fused_qkv(full.qweight, full.scales, full.scaled_zeros, full.bias, *qkv_split, rank, world)
+        self.local = _from_tensors(*t, full.group_size)
+
+    def forward(self, x):
+        return self.local(x)
+
+
+class RowParallelWQLinear(nn.Module):
+    """y = sum over ranks of x[:, k-slice of this rank] @ W[:, k-slice]^T: the local kernel, then ONE
+    all-reduce(sum) of the [tokens, out_features] partials.  The bias is added after the reduction."""
+
+    def __init__(self, full: WQLinear, rank, world, group=None):
+        super().__init__()
+        t = shard_row(full.qweight, full.scales, full.scaled_zeros, rank, world, full.group_size)
+        self.local = _from_tensors(*t, None, full.group_size)
+        self.bias = full.bias
+        self.group = group
+        self.world = world
+
+    def forward(self, x_local):
+        y = self.local(x_local)
+        if self.world > 1:
+            torch.distributed.all_reduce(y, op=torch.distributed.ReduceOp.SUM, group=self.group)
+        return y + self.bias if self.bias is not None else y

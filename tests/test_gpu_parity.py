@@ -110,7 +110,8 @@ def test_gemm_linearity_and_determinism_full_size():
     _, y2 = abi_call(P.lib(), x, qw, s, z, M, N, K, dtype, "gemm")
     assert torch.equal(y1, y2)                                  # no atomics, fixed reduction order
     _, yh = abi_call(P.lib(), (x * 2).contiguous(), qw, s, z, M, N, K, dtype, "gemm")
-    assert torch.equal(yh.float(), y1.float() * 2)              # scaling by 2 is exact in fp16 / fp32 (no overflow here)
+    big = y1.abs() > 2.0 ** -13                                  # fp16 subnormal outputs lose a bit when halved
+    assert torch.equal(yh.float()[big], y1.float()[big] * 2)    # scaling by 2 is exact in fp16 / fp32 (no overflow here)
     # rows of the batch are independent: a token computed alone through the decode path agrees
     _, y_row = abi_call(P.lib(), x[1000:1001].contiguous(), qw, s, z, 1, N, K, dtype, "gemv")
     assert rel_err(np64(y_row), np64(y1[1000:1001])) < 5e-4

@@ -53,6 +53,7 @@ b200awq::StreamTuning stream_tuning() {
   t.mode = env_int("B200AWQ_STREAM_MODE", -1);
   t.kc = env_int("B200AWQ_STREAM_KC", 0);
   t.rpb = env_int("B200AWQ_STREAM_RPB", 0);
+  t.pad = env_int("B200AWQ_STREAM_PAD", 0);
   return t;
 }
 b200awq::UmmaTuning umma_tuning() {

@@ -10,7 +10,8 @@ namespace b200awq {
 struct StreamTuning {
   int mode = -1;  // -1 = auto (fp16: 2, bf16: 0); 0 operand-exact, 2 group-factored    [env B200AWQ_STREAM_MODE]
   int kc = 0;     // 0 = auto, else input channels per CTA (K / kc in {1,2,4,8})       [env B200AWQ_STREAM_KC]
-  int rpb = 0;    // 0 = auto, else 512-k rounds per prefetch barrier (copy = rpb KB)   [env B200AWQ_STREAM_RPB]
+  int rpb = 0;    // 0 = auto, else 1024-k rounds per prefetch barrier (copy = 2 rpb KB) [env B200AWQ_STREAM_RPB]
+  int pad = 0;    // extra dynamic smem bytes per CTA (co-residency limiter, tuning)     [env B200AWQ_STREAM_PAD]
 };
 
 struct UmmaTuning {

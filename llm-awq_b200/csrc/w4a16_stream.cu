@@ -35,6 +35,8 @@
 //             y += s*(acc - C) + z*X,   X = sum_k x_k,  C = 1024*X_lo + 64*X_hi  (bf16: 128*X).
 //         Exact in the integer q; differs from MODE 0 only by not rounding q*s+z to T.
 //         Default for fp16 (that rounding is 2^-12 relative: ~2e-4 normwise, inside 1e-3).
+#include <algorithm>
+
 #include "w4_common.cuh"
 #include "w4a16_kernels.h"
 
@@ -61,6 +63,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 
 struct StreamSmem {
   int w, s, z, x, red, cpart, xsum, bars, total;
+  int ngroups, nrounds, nbar;  // derived on the host so the kernel prologue has no integer divisions
 };
 
 __host__ __device__ inline StreamSmem stream_smem_layout(int RO, int TT, int MODE, int M, int Kc, int rpb) {
@@ -78,6 +81,9 @@ __host__ __device__ inline StreamSmem stream_smem_layout(int RO, int TT, int MOD
   L.xsum = off, off += (MODE ? 8 * TT * ng * 8 : 0);
   L.bars = off, off += (nbar + 1) * 8;
   L.total = off;
+  L.ngroups = ng;
+  L.nrounds = (ng + kStreamWarps - 1) / kStreamWarps;
+  L.nbar = nbar;
   return L;
 }
 
@@ -87,9 +93,10 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 template <typename T, int RO, int TT, int MODE>
-__global__ void __launch_bounds__(kStreamThreads, TT == 1 ? 3 : 2)
+__global__ void __launch_bounds__(kStreamThreads, TT == 1 ? 4 : 2)
 w4a16_stream_kernel(const T* __restrict__ x, const uint16_t* __restrict__ qw, const T* __restrict__ scales,
-                    const T* __restrict__ szeros, T* __restrict__ y, int M, int N, int K, int Kc, int S, int rpb, int seq) {
+                    const T* __restrict__ szeros, T* __restrict__ y, int M, int N, int K, int Kc, int S, int rpb, int seq,
+                    const __grid_constant__ StreamSmem L) {
   B200AWQ_STAMP(0);
   constexpr bool kBf16 = TypeTraits<T>::kIsBf16;
   constexpr int R = 8 * RO;  // output channels per CTA
@@ -97,15 +104,12 @@ w4a16_stream_kernel(const T* __restrict__ x, const uint16_t* __restrict__ qw, co
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, tig = lane & 3;
   const int rank = (S > 1) ? (int)cluster_ctarank() : 0;
-  const int rb = blockIdx.x / S;
+  const int rb = (S > 1) ? (int)(blockIdx.x / S) : (int)blockIdx.x;
   const int n0 = rb * R;
   const int kbase = rank * Kc;
-  const int ngroups = Kc / kGroup;
-  const int nrounds = (ngroups + kStreamWarps - 1) / kStreamWarps;
-  const int nbar = (nrounds + rpb - 1) / rpb;
+  const int ngroups = L.ngroups, nrounds = L.nrounds, nbar = L.nbar;
   const int wrow = Kc * 2;       // bytes of one 4-row quad over this CTA's k range
   const int xrow = Kc * 2 + 16;  // padded activation row (bank spread between tokens)
-  const StreamSmem L = stream_smem_layout(RO, TT, MODE, M, Kc, rpb);
 
   uint8_t* wbuf = smem + L.w;
   uint16_t* sbuf = reinterpret_cast<uint16_t*>(smem + L.s);  // [group][R]
@@ -122,6 +126,7 @@ w4a16_stream_kernel(const T* __restrict__ x, const uint16_t* __restrict__ qw, co
     for (int b = 0; b <= nbar; ++b) mbar_init(&bars[b], 1);
     mbar_fence_init();
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    B200AWQ_STAMP(7);
     const int piece = rpb * kRoundK * 2;  // bytes per quad row per barrier
     for (int b = 0; b < nbar; ++b) {
       const int off = b * piece;
@@ -368,6 +373,8 @@ extern "C" int b200awq_debug_read_trace(unsigned long long* host, int count) {
 // ------------------------------------------------------------------------------------ host
 constexpr int kStreamSmemCap = 200 * 1024;
 
+int g_stream_pad = 0;  // extra dynamic shared memory per CTA: limits co-residency (tuning knob B200AWQ_STREAM_PAD)
+
 static int next_seq() {
   static int seq = 0;
   return seq++;
@@ -396,7 +403,7 @@ static int launch_stream_t(const void* x, const void* qw, const void* sc, const 
   if (L.total > kStreamSmemCap) return B200AWQ_ERR_SHAPE;
   auto kern = w4a16_stream_kernel<T, RO, TT, MODE>;
   static bool attr_set = false;  // per instantiation
-  if (L.total > 48 * 1024 && !attr_set) {
+  if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemCap);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
@@ -404,7 +411,17 @@ static int launch_stream_t(const void* x, const void* qw, const void* sc, const 
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(N / (8 * RO)) * S);
   cfg.blockDim = dim3(kStreamThreads);
-  cfg.dynamicSmemBytes = L.total;
+  // Co-residency: a launch that fits in one wave runs fastest with FEW CTAs per SM (the next launch's
+  // CTAs only need enough room to prefetch); multi-wave launches want as many as fit (measured).
+  size_t dyn = L.total;
+  const int ctas = (N / (8 * RO)) * S;
+  const int per_sm = ctas <= 2 * 148 ? 2 : (ctas <= 3 * 148 ? 3 : 0);
+  if (g_stream_pad > 0)
+    dyn += (size_t)g_stream_pad;
+  else if (g_stream_pad == 0 && per_sm > 0 && S == 1)
+    dyn = std::max(dyn, (size_t)(233472 / (per_sm + 1) - 512));
+  if (dyn > (size_t)kStreamSmemCap) dyn = L.total;
+  cfg.dynamicSmemBytes = dyn;
   cfg.stream = stream;
   cudaLaunchAttribute attrs[2];
   int na = 0;
@@ -423,7 +440,7 @@ static int launch_stream_t(const void* x, const void* qw, const void* sc, const 
   cfg.attrs = attrs;
   cfg.numAttrs = na;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, (const T*)x, (const uint16_t*)qw, (const T*)sc, (const T*)sz, (T*)y, M, N,
-                                     K, Kc, S, rpb, next_seq());
+                                     K, Kc, S, rpb, next_seq(), L);
   return e == cudaSuccess ? 0 : (int)e;
 }
 
@@ -444,7 +461,8 @@ int launch_stream(const void* x, const void* qw, const void* sc, const void* sz,
   const int ro = (N % 16 == 0) ? 2 : 1;
   const int kc_target = M <= 2 ? 4096 : (M <= 8 ? 2048 : 1024);
   const int S = pick_splits(K, kc_target, tune.kc);
-  const int rpb = tune.rpb > 0 ? tune.rpb : 1;
+  const int rpb = tune.rpb > 0 ? tune.rpb : 64;  // default: one barrier (4 large copies) per CTA
+  g_stream_pad = tune.pad;  // > 0: explicit extra bytes, 0: heuristic, < 0: none
   // default arithmetic: fp16 -> group-factored (MODE 2), bf16 -> operand-exact (MODE 0); see the header comment
   const int mode = (tune.mode == 0 || tune.mode == 2) ? tune.mode : (dtype == B200AWQ_DTYPE_F16 ? 2 : 0);
   if (dtype == B200AWQ_DTYPE_F16) {

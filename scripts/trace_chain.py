@@ -60,12 +60,12 @@ def dump(tag):
     # pick 6 consecutive launches with the largest seq values present (the last chain executed)
     seqs = sorted(range(1024), key=lambda s: int(t[s, 0, 0]))[-CH:]
     seqs = seqs[CH // 2: CH // 2 + 6]
-    print(f"[{tag}] ABSOLUTE stamps (us): start | issued | pre-wait | wait-ret | x-ready | loop-end | end")
+    print(f"[{tag}] ABSOLUTE stamps (us): start | issued | pre-wait | wait-ret | x-ready | loop-end | end | bar-init")
     t0 = int(t[seqs[0], 0, 0])
     for s in seqs:
         for c in (0, 1):
             r = t[s, c]
-            print(f"  seq {s:4d} cta {'first' if c == 0 else 'last '}: " + " ".join(f"{(int(r[i]) - t0) / 1e3:7.2f}" for i in range(7)))
+            print(f"  seq {s:4d} cta {'first' if c == 0 else 'last '}: " + " ".join(f"{(int(r[i]) - t0) / 1e3:7.2f}" for i in range(8)))
 
 
 s = torch.cuda.Stream()

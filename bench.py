@@ -34,6 +34,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 LLAMA3_8B = dict(name="Llama-3-8B", hidden=4096, inter=14336, q_heads=32, kv_heads=8, head_dim=128, layers=32)
+LLAMA2_70B = dict(name="Llama-2-70B", hidden=8192, inter=28672, q_heads=64, kv_heads=8, head_dim=128, layers=80)
 METRIC = "Llama-3-8B W4A16 g128 decode tok/s (linear path), 1xB200"
 UNIT = "tok/s"
 G = 128
@@ -123,11 +124,23 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ model
-def build_model(torch, cfg, dtype, device, layers=None):
+def tp_projs(cfg, tp):
+    """Per-rank shapes under tensor parallelism: qkv / gate / up column-parallel
+    (N / tp), o / down row-parallel (K / tp, followed by ONE all-reduce)."""
+    out = []
+    for name, K, N in layer_projs(cfg):
+        if name in ("o", "down"):
+            out.append((name, K // tp, N))
+        else:
+            out.append((name, K, N // tp))
+    return out
+
+
+def build_model(torch, cfg, dtype, device, layers=None, projs=None):
     """Packed weights of every quantised linear, generated on the device (SURVEY.md §8d generator)."""
     out = []
     for l in range(cfg["layers"] if layers is None else layers):
-        for p, (name, K, N) in enumerate(layer_projs(cfg)):
+        for p, (name, K, N) in enumerate(projs or layer_projs(cfg)):
             g = torch.Generator(device=device).manual_seed(1234 + 97 * l + p)
             qw = torch.randint(-32768, 32768, (N // 4, K), generator=g, dtype=torch.int32, device=device).to(torch.int16)
             rows, ng = scale_rows(K), K // G
@@ -339,6 +352,66 @@ def run_b200(args):
     print(json.dumps(line))
 
 
+def run_tp70b(args):
+    """BASELINE configs[3]: Llama-2-70B W4A16 decode bs=1, tensor-parallel over the N ranks of this launch.
+    Per layer and rank: qkv (col) -> o (row, all-reduce) -> gate, up (col) -> down (row, all-reduce); the
+    160 all-reduces of one token are 16 KB each (latency-bound).  Total work is fixed: "strong" scaling."""
+    import torch
+    import llm_awq_b200 as P
+    rank, world, local, dist = dist_setup(torch, args.gpus)
+    device = torch.device("cuda", local)
+    dtype = torch.float16
+    lib = P.lib()
+    cfg = LLAMA2_70B
+    peaks = read_peaks()
+    projs = tp_projs(cfg, world)
+    model = build_model(torch, cfg, dtype, device, projs=projs)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    xs = {K: (torch.randn(1, K, device=device) * 0.25).to(dtype) for K in {m["K"] for m in model}}
+    ys = {(m["name"], m["N"]): torch.empty(1, m["N"], dtype=dtype, device=device) for m in model}
+
+    def step(with_comm):
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        for m in model:
+            y = ys[(m["name"], m["N"])]
+            rc = lib.b200awq_w4a16_gemv(p(xs[m["K"]]), p(m["qw"]), p(m["sc"]), p(m["sz"]), p(y), 1, m["N"], m["K"], G, 0, st)
+            if rc != 0:
+                raise RuntimeError(lib.b200awq_strerror(rc).decode())
+            if with_comm and dist is not None and m["name"] in ("o", "down"):
+                dist.all_reduce(y)
+
+    def graph(with_comm):
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            step(with_comm)
+        s.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            step(with_comm)
+        return g
+    g_full = graph(True)
+    ms_full, _ = timed_steps(torch, dist, device, g_full.replay, args.steps, args.warmup)
+    g_nocomm = graph(False)
+    ms_nc, _ = timed_steps(torch, dist, device, g_nocomm.replay, args.steps, args.warmup)
+    if rank != 0:
+        return
+    step_ms = ms_full / args.steps
+    bytes_rank = sum(alg_bytes(1, m["N"], m["K"]) for m in model)
+    print(json.dumps({
+        "metric": "Llama-2-70B W4A16 g128 decode tok/s (linear path), TP=%d" % world, "value": 1000.0 / step_ms, "unit": UNIT,
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "config": {"workload": "Llama-2-70B W4A16 g128 decode bs=1, TP=%d (BASELINE configs[3])" % world,
+                   "parallelism": "tp%d: column-parallel qkv/gate/up, row-parallel o/down + 1 NCCL all-reduce each" % world,
+                   "launches_per_step": len(model), "allreduces_per_step": 0 if world == 1 else 2 * cfg["layers"],
+                   "allreduce_bytes": cfg["hidden"] * 2, "l2": "inputs larger than L2"},
+        "comm": {"ms_per_step_without_allreduce": ms_nc / args.steps, "ms_per_step_allreduce": step_ms - ms_nc / args.steps},
+        "gpu_launches": len(model) * args.steps,
+        "roofline": {"bound": "hbm", "achieved": bytes_rank / (step_ms * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                     "frac": bytes_rank / (step_ms * 1e-3) / 1e9 / peaks["hbm"], "traffic": None, "per": "rank",
+                     "frac_without_allreduce": bytes_rank / (ms_nc / args.steps * 1e-3) / 1e9 / peaks["hbm"]}}))
+
+
 def cpu_layer(torch, layers=1):
     """One decoder layer's five WQLinear forwards (M = 1) on the host: the bounded CPU sample."""
     from oracle import cpu_path
@@ -451,12 +524,15 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=30)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-ref-gpu", dest="ref_gpu", action="store_false")
+    ap.add_argument("--workload", default="llama3", choices=["llama3", "tp70b"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference(args)
     elif args.impl == "reference-gpu":
         run_reference_gpu(args)
+    elif args.workload == "tp70b":
+        run_tp70b(args)
     else:
         run_b200(args)
 

@@ -56,6 +56,21 @@ b200awq::StreamTuning stream_tuning() {
   t.pad = env_int("B200AWQ_STREAM_PAD", 0);
   return t;
 }
+b200awq::FlatTuning flat_tuning() {
+  b200awq::FlatTuning t;
+  t.kc = env_int("B200AWQ_FLAT_KC", 0);
+  return t;
+}
+// which kernel serves small token counts: B200AWQ_SKINNY = "flat" (tcgen05, default) | "stream" (mma.sync)
+bool use_flat(int m, int n) {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* v = std::getenv("B200AWQ_SKINNY");
+    mode = (v && v[0] == 's') ? 0 : 1;
+  }
+  // measured crossovers (profiles/): the mma.sync streaming kernel wins for m <= 4, the tcgen05 kernels above
+  return mode == 1 && n % 128 == 0 && m >= env_int("B200AWQ_FLAT_MIN_M", 5) && m <= env_int("B200AWQ_FLAT_MAX_M", 16);
+}
 b200awq::UmmaTuning umma_tuning() {
   b200awq::UmmaTuning t;
   t.tn = env_int("B200AWQ_UMMA_TN", 0);
@@ -71,8 +86,13 @@ int b200awq_w4a16_gemv(const void* x, const void* qweight, const void* scales, c
                        int k, int group_size, int dtype, void* stream) {
   if (int e = check_common(x, qweight, scales, szeros, y, m, n, k, group_size, dtype)) return e;
   if (m > 7) return B200AWQ_ERR_BATCH;  // reference envelope: gemv_cuda.cu:291-330
-  int r = b200awq::launch_stream(x, qweight, scales, szeros, y, m, n, k, dtype, pdl_enabled(), stream_tuning(),
-                                 static_cast<cudaStream_t>(stream));
+  int r = B200AWQ_ERR_SHAPE;
+  if (use_flat(m, n))
+    r = b200awq::launch_flat(x, qweight, scales, szeros, y, m, n, k, dtype, pdl_enabled(), flat_tuning(),
+                             static_cast<cudaStream_t>(stream));
+  if (r == B200AWQ_ERR_SHAPE)
+    r = b200awq::launch_stream(x, qweight, scales, szeros, y, m, n, k, dtype, pdl_enabled(), stream_tuning(),
+                               static_cast<cudaStream_t>(stream));
   if (r == 0) g_launches.fetch_add(1, std::memory_order_relaxed);
   return r;
 }
@@ -87,7 +107,10 @@ int b200awq_w4a16_gemm(const void* x, const void* qweight, const void* scales, c
   if (n % 128) return B200AWQ_ERR_SHAPE;  // reference: N / CTA_N with CTA_N = 128, gemm_cuda.cu:38,1225
   const int stream_max_m = env_int("B200AWQ_STREAM_MAX_M", 16);
   int r = B200AWQ_ERR_SHAPE;
-  if (m <= stream_max_m && m <= 16)
+  if (use_flat(m, n))
+    r = b200awq::launch_flat(x, qweight, scales, szeros, y, m, n, k, dtype, pdl_enabled(), flat_tuning(),
+                             static_cast<cudaStream_t>(stream));
+  if (r == B200AWQ_ERR_SHAPE && m <= stream_max_m && m <= 16)
     r = b200awq::launch_stream(x, qweight, scales, szeros, y, m, n, k, dtype, pdl_enabled(), stream_tuning(),
                                static_cast<cudaStream_t>(stream));
   if (r == B200AWQ_ERR_SHAPE)  // too many tokens for the streaming kernel (or its k slice does not fit on chip)

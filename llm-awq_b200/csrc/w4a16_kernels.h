@@ -19,6 +19,10 @@ struct UmmaTuning {
   int max_ctas = 0;  // 0 = one per SM                                   [env B200AWQ_UMMA_CTAS]
 };
 
+struct FlatTuning {
+  int kc = 0;  // 0 = auto, else input channels per CTA (K / kc <= 8)   [env B200AWQ_FLAT_KC]
+};
+
 // HBM-bound streaming kernel, 1 <= M <= 16 (w4a16_stream.cu)
 int launch_stream(const void* x, const void* qw, const void* sc, const void* sz, void* y, int M, int N, int K, int dtype,
                   bool pdl, const StreamTuning& tune, cudaStream_t stream);
@@ -26,5 +30,9 @@ int launch_stream(const void* x, const void* qw, const void* sc, const void* sz,
 // tcgen05 / TMA / TMEM tensor-core kernel, any M (w4a16_umma.cu)
 int launch_umma(const void* x, const void* qw, const void* sc, const void* sz, void* y, int M, int N, int K, int dtype,
                 bool pdl, const UmmaTuning& tune, cudaStream_t stream);
+
+// tcgen05 skinny-batch kernel, 1 <= M <= 64, N % 128 == 0 (w4a16_flat.cu)
+int launch_flat(const void* x, const void* qw, const void* sc, const void* sz, void* y, int M, int N, int K, int dtype,
+                bool pdl, const FlatTuning& tune, cudaStream_t stream);
 
 }  // namespace b200awq

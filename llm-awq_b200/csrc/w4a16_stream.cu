@@ -48,7 +48,7 @@ constexpr int kRoundK = kStreamWarps * kGroup;  // input channels consumed per r
 
 #ifdef B200AWQ_TRACE
 // Debug build only (scripts/trace_chain.py): wall-clock stamps of the first and last CTA of each launch.
-__device__ unsigned long long g_trace_buf[1024 * 2 * 8];
+__device__ unsigned long long g_trace_buf[1024 * 2 * 8];  // shared with w4a16_flat.cu (needs -rdc)
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -352,9 +352,13 @@ w4a16_stream_kernel(const T* __restrict__ x, const uint16_t* __restrict__ qw, co
       for (int e = tid; e < TT * 128; e += kStreamThreads) {
         const int t = e >> 7, row = (e >> 3) & 15, tok = 8 * t + (e & 7);
         if (tok < M && row < R) {
-          float v = 0.f;
           const uint32_t a = smem_u32(&cpart[e]);
-          for (int r = 0; r < S; ++r) v += ld_cluster_f32(map_to_rank(a, (uint32_t)r));
+          float pv[8];  // all remote loads in flight at once (cluster size <= 8), then a fixed-order sum
+#pragma unroll
+          for (int r = 0; r < 8; ++r) pv[r] = (r < S) ? ld_cluster_f32(map_to_rank(a, (uint32_t)r)) : 0.f;
+          float v = 0.f;
+#pragma unroll
+          for (int r = 0; r < 8; ++r) v += pv[r];
           y[(size_t)tok * N + n0 + row] = from_float<T>(v);
         }
       }

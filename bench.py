@@ -370,29 +370,41 @@ def run_tp70b(args):
     xs = {K: (torch.randn(1, K, device=device) * 0.25).to(dtype) for K in {m["K"] for m in model}}
     ys = {(m["name"], m["N"]): torch.empty(1, m["N"], dtype=dtype, device=device) for m in model}
 
-    def step(with_comm):
+    ex = None
+    if world > 1:
+        from llm_awq_b200 import tp
+        ex = tp.PeerExchange(1, cfg["hidden"])
+
+    def step(mode):
+        """mode: "none" (no reduction, timing reference) | "nccl" (kernel + NCCL all-reduce) | "fused" (one kernel)"""
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         for m in model:
             y = ys[(m["name"], m["N"])]
-            rc = lib.b200awq_w4a16_gemv(p(xs[m["K"]]), p(m["qw"]), p(m["sc"]), p(m["sz"]), p(y), 1, m["N"], m["K"], G, 0, st)
+            a = (p(xs[m["K"]]), p(m["qw"]), p(m["sc"]), p(m["sz"]), p(y), 1, m["N"], m["K"], G, 0)
+            if mode == "fused" and m["name"] in ("o", "down"):
+                rc = lib.b200awq_w4a16_gemv_allreduce(*a, ex.ptr, st)
+            else:
+                rc = lib.b200awq_w4a16_gemv(*a, st)
             if rc != 0:
                 raise RuntimeError(lib.b200awq_strerror(rc).decode())
-            if with_comm and dist is not None and m["name"] in ("o", "down"):
+            if mode == "nccl" and dist is not None and m["name"] in ("o", "down"):
                 dist.all_reduce(y)
 
-    def graph(with_comm):
+    def graph(mode):
         s = torch.cuda.Stream()
         with torch.cuda.stream(s):
-            step(with_comm)
+            step(mode)
         s.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            step(with_comm)
+            step(mode)
         return g
-    g_full = graph(True)
-    ms_full, _ = timed_steps(torch, dist, device, g_full.replay, args.steps, args.warmup)
-    g_nocomm = graph(False)
-    ms_nc, _ = timed_steps(torch, dist, device, g_nocomm.replay, args.steps, args.warmup)
+    ms_nc, _ = timed_steps(torch, dist, device, graph("none").replay, args.steps, args.warmup)
+    ms_nccl = ms_fused = None
+    if world > 1:
+        ms_nccl, _ = timed_steps(torch, dist, device, graph("nccl").replay, args.steps, args.warmup)
+        ms_fused, _ = timed_steps(torch, dist, device, graph("fused").replay, args.steps, args.warmup)
+    ms_full = ms_nc if world == 1 else min(ms_nccl, ms_fused)
     if rank != 0:
         return
     step_ms = ms_full / args.steps
@@ -402,10 +414,13 @@ def run_tp70b(args):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
         "config": {"workload": "Llama-2-70B W4A16 g128 decode bs=1, TP=%d (BASELINE configs[3])" % world,
-                   "parallelism": "tp%d: column-parallel qkv/gate/up, row-parallel o/down + 1 NCCL all-reduce each" % world,
+                   "parallelism": "tp%d: column-parallel qkv/gate/up, row-parallel o/down + 1 all-reduce each (NCCL, or fused into the GEMV over NVLink peer memory)" % world,
                    "launches_per_step": len(model), "allreduces_per_step": 0 if world == 1 else 2 * cfg["layers"],
                    "allreduce_bytes": cfg["hidden"] * 2, "l2": "inputs larger than L2"},
-        "comm": {"ms_per_step_without_allreduce": ms_nc / args.steps, "ms_per_step_allreduce": step_ms - ms_nc / args.steps},
+        "comm": {"ms_per_step_without_allreduce": ms_nc / args.steps,
+                 "ms_per_step_nccl_allreduce": None if ms_nccl is None else ms_nccl / args.steps,
+                 "ms_per_step_fused_nvlink_exchange": None if ms_fused is None else ms_fused / args.steps,
+                 "headline_uses": "single GPU" if world == 1 else ("fused" if ms_fused <= ms_nccl else "nccl")},
         "gpu_launches": len(model) * args.steps,
         "roofline": {"bound": "hbm", "achieved": bytes_rank / (step_ms * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
                      "frac": bytes_rank / (step_ms * 1e-3) / 1e9 / peaks["hbm"], "traffic": None, "per": "rank",
@@ -535,6 +550,12 @@ def main():
         run_tp70b(args)
     else:
         run_b200(args)
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:  # noqa: BLE001
+        pass
 
 
 if __name__ == "__main__":

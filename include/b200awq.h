@@ -52,6 +52,7 @@ extern "C" {
 #define B200AWQ_ERR_WORKSPACE (-6) /* workspace smaller than b200awq_w4a16_gemm_workspace_bytes */
 #define B200AWQ_ERR_DRIVER (-7)    /* CUDA driver entry point for TMA descriptors unavailable */
 #define B200AWQ_ERR_DEVICE (-8)    /* current device is not compute capability 10.x */
+#define B200AWQ_ERR_PEERS (-9)     /* bad peer description (world, rank, capacities, null buffers) */
 
 /* Decode path: 1 <= m <= 7 (the reference's GEMV envelope).  n % 8 == 0, k % 128 == 0,
  * group_size == 128. */
@@ -66,6 +67,28 @@ int b200awq_w4a16_gemm(const void* x, const void* qweight, const void* scales, c
                        void* workspace, size_t workspace_bytes, void* stream);
 
 size_t b200awq_w4a16_gemm_workspace_bytes(int m, int n, int k);
+
+/* Row-parallel tensor parallelism (new work; the reference has no multi-GPU path): the decode
+ * GEMV of THIS rank's k-slice fused with the sum all-reduce of the [m, n] partial outputs over NVLink peer
+ * memory, in one kernel.  Every rank calls it with its own shard and the same (m, n); on return (stream order)
+ * y holds the full sum on every rank, bit-identical across ranks.
+ *   data[r]   rank r's exchange buffer as mapped in this process (symmetric / peer-mapped allocation),
+ *             fp32, >= 2 * world * cap_floats elements, any content
+ *   flags[r]  rank r's flag words (uint32), >= 2 * world * cap_flags elements, ZERO before the first call
+ *   epoch     this rank's private counters (device memory, uint32, >= cap_flags elements, ZERO before first use)
+ *   cap_floats >= m * n, cap_flags >= n / 8.  1 <= m <= 8, world <= 8.  All ranks must issue the same
+ *   sequence of calls on these buffers.  Safe under CUDA-graph capture / replay (no host-side state). */
+typedef struct b200awq_peers {
+  void* data[8];
+  void* flags[8];
+  void* epoch;
+  int rank, world;
+  int cap_floats, cap_flags;
+} b200awq_peers;
+
+int b200awq_w4a16_gemv_allreduce(const void* x, const void* qweight, const void* scales, const void* szeros,
+                                 void* y, int m, int n, int k, int group_size, int dtype,
+                                 const b200awq_peers* peers, void* stream);
 
 /* Names used by BASELINE.json's north_star; identical to the two launchers above. */
 int gemv_forward_4bit(const void* x, const void* qweight, const void* scales, const void* szeros,

@@ -54,6 +54,8 @@ b200awq::StreamTuning stream_tuning() {
   t.kc = env_int("B200AWQ_STREAM_KC", 0);
   t.rpb = env_int("B200AWQ_STREAM_RPB", 0);
   t.pad = env_int("B200AWQ_STREAM_PAD", 0);
+  t.rbs = env_int("B200AWQ_STREAM_RBS", 0);
+  t.warps = env_int("B200AWQ_STREAM_WARPS", 0);
   return t;
 }
 b200awq::FlatTuning flat_tuning() {
@@ -93,6 +95,31 @@ int b200awq_w4a16_gemv(const void* x, const void* qweight, const void* scales, c
   if (r == B200AWQ_ERR_SHAPE)
     r = b200awq::launch_stream(x, qweight, scales, szeros, y, m, n, k, dtype, pdl_enabled(), stream_tuning(),
                                static_cast<cudaStream_t>(stream));
+  if (r == 0) g_launches.fetch_add(1, std::memory_order_relaxed);
+  return r;
+}
+
+int b200awq_w4a16_gemv_allreduce(const void* x, const void* qweight, const void* scales, const void* szeros, void* y, int m,
+                                 int n, int k, int group_size, int dtype, const b200awq_peers* peers, void* stream) {
+  if (int e = check_common(x, qweight, scales, szeros, y, m, n, k, group_size, dtype)) return e;
+  if (m > 8) return B200AWQ_ERR_BATCH;
+  if (!peers || peers->world < 1 || peers->world > 8 || peers->rank < 0 || peers->rank >= peers->world || !peers->epoch ||
+      (long long)peers->cap_floats < (long long)m * n || peers->cap_flags < n / 8)
+    return B200AWQ_ERR_PEERS;
+  b200awq::PeerArgs pa{};
+  for (int r = 0; r < peers->world; ++r) {
+    if (!peers->data[r] || !peers->flags[r]) return B200AWQ_ERR_PEERS;
+    pa.data[r] = static_cast<float*>(peers->data[r]);
+    pa.flags[r] = static_cast<unsigned int*>(peers->flags[r]);
+  }
+  pa.epoch = static_cast<unsigned int*>(peers->epoch);
+  pa.rank = peers->rank;
+  pa.world = peers->world;
+  pa.cap = peers->cap_floats;
+  pa.cap_flags = peers->cap_flags;
+  pa.dbg = env_int("B200AWQ_FUSED_DBG", 0);
+  int r = b200awq::launch_stream(x, qweight, scales, szeros, y, m, n, k, dtype, pdl_enabled(), stream_tuning(),
+                                 static_cast<cudaStream_t>(stream), &pa);
   if (r == 0) g_launches.fetch_add(1, std::memory_order_relaxed);
   return r;
 }
@@ -148,6 +175,7 @@ const char* b200awq_strerror(int code) {
     case B200AWQ_ERR_WORKSPACE: return "workspace too small";
     case B200AWQ_ERR_DRIVER: return "cuTensorMapEncodeTiled unavailable or failed";
     case B200AWQ_ERR_DEVICE: return "device is not compute capability 10.x (sm_100a kernels only)";
+    case B200AWQ_ERR_PEERS: return "bad peer description for the fused all-reduce";
     default: return code > 0 ? cudaGetErrorString(static_cast<cudaError_t>(code)) : "unknown error";
   }
 }

@@ -11,6 +11,8 @@ struct StreamTuning {
   int mode = -1;  // -1 = auto (fp16: 2, bf16: 0); 0 operand-exact, 2 group-factored    [env B200AWQ_STREAM_MODE]
   int kc = 0;     // 0 = auto, else input channels per CTA (K / kc in {1,2,4,8})       [env B200AWQ_STREAM_KC]
   int rpb = 0;    // 0 = auto, else 1024-k rounds per prefetch barrier (copy = 2 rpb KB) [env B200AWQ_STREAM_RPB]
+  int rbs = 0;    // 0 = auto, else row blocks per CTA (1 or 2)                        [env B200AWQ_STREAM_RBS]
+  int warps = 0;  // 0 = auto, else 8 or 16 warps per CTA                              [env B200AWQ_STREAM_WARPS]
   int pad = 0;    // extra dynamic smem bytes per CTA (co-residency limiter, tuning)     [env B200AWQ_STREAM_PAD]
 };
 
@@ -19,13 +21,25 @@ struct UmmaTuning {
   int max_ctas = 0;  // 0 = one per SM                                   [env B200AWQ_UMMA_CTAS]
 };
 
+// Row-parallel tensor parallelism: the GEMV epilogue exchanges fp32 partial sums with the peer GPUs through
+// symmetric (peer-mapped) buffers over NVLink and reduces them in the same kernel (w4a16_stream.cu).
+struct PeerArgs {
+  float* data[8];           // data[r]: rank r's exchange buffer as mapped in this process
+  unsigned int* flags[8];   // flags[r]: rank r's flag words
+  unsigned int* epoch;      // this rank's per-row-block epoch counters (device memory, zero-initialised once)
+  int rank, world;          // world == 0: no exchange
+  int cap;                  // floats per (parity, source) region  (>= m * n)
+  int cap_flags;            // flag words per (parity, source) region (>= n / 8)
+  int dbg;                  // tuning probes (env B200AWQ_FUSED_DBG): 1 no flag wait, 2 local writes only, 4 no system fence
+};
+
 struct FlatTuning {
   int kc = 0;  // 0 = auto, else input channels per CTA (K / kc <= 8)   [env B200AWQ_FLAT_KC]
 };
 
 // HBM-bound streaming kernel, 1 <= M <= 16 (w4a16_stream.cu)
 int launch_stream(const void* x, const void* qw, const void* sc, const void* sz, void* y, int M, int N, int K, int dtype,
-                  bool pdl, const StreamTuning& tune, cudaStream_t stream);
+                  bool pdl, const StreamTuning& tune, cudaStream_t stream, const PeerArgs* peers = nullptr);
 
 // tcgen05 / TMA / TMEM tensor-core kernel, any M (w4a16_umma.cu)
 int launch_umma(const void* x, const void* qw, const void* sc, const void* sz, void* y, int M, int N, int K, int dtype,

@@ -42,9 +42,6 @@
 
 namespace b200awq {
 
-constexpr int kStreamThreads = 256;
-constexpr int kStreamWarps = 8;
-constexpr int kRoundK = kStreamWarps * kGroup;  // input channels consumed per round of the 4 warps
 
 #ifdef B200AWQ_TRACE
 // Debug build only (scripts/trace_chain.py): wall-clock stamps of the first and last CTA of each launch.
@@ -64,26 +61,28 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 struct StreamSmem {
   int w, s, z, x, red, cpart, xsum, bars, total;
   int ngroups, nrounds, nbar;  // derived on the host so the kernel prologue has no integer divisions
+  int rbs;                     // row blocks (of 8*RO channels) this CTA processes one after the other
 };
 
-__host__ __device__ inline StreamSmem stream_smem_layout(int RO, int TT, int MODE, int M, int Kc, int rpb) {
+__host__ __device__ inline StreamSmem stream_smem_layout(int RO, int TT, int MODE, int M, int Kc, int rpb, int rbs, int kStreamWarps) {
   StreamSmem L;
   const int ng = Kc / kGroup;
   const int nbar = ((ng + kStreamWarps - 1) / kStreamWarps + rpb - 1) / rpb;
   int off = 0;
-  L.w = off, off += 2 * RO * Kc * 2;
-  L.s = off, off += ng * 8 * RO * 2;
-  L.z = off, off += ng * 8 * RO * 2;
+  L.w = off, off += rbs * 2 * RO * Kc * 2;
+  L.s = off, off += rbs * ng * 8 * RO * 2;
+  L.z = off, off += rbs * ng * 8 * RO * 2;
   off = (off + 15) & ~15;
   L.x = off, off += M * (Kc * 2 + 16);
   L.red = off, off += kStreamWarps * TT * 128 * 4;
   L.cpart = off, off += TT * 128 * 4;
   L.xsum = off, off += (MODE ? 8 * TT * ng * 8 : 0);
-  L.bars = off, off += (nbar + 1) * 8;
+  L.bars = off, off += (rbs * nbar + 1) * 8;
   L.total = off;
   L.ngroups = ng;
   L.nrounds = (ng + kStreamWarps - 1) / kStreamWarps;
   L.nbar = nbar;
+  L.rbs = rbs;
   return L;
 }
 
@@ -92,20 +91,22 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-template <typename T, int RO, int TT, int MODE>
-__global__ void __launch_bounds__(kStreamThreads, TT == 1 ? 4 : 2)
+template <typename T, int RO, int TT, int MODE, int kStreamWarps>
+__global__ void __launch_bounds__(kStreamWarps * 32, TT == 1 ? (kStreamWarps == 16 ? 2 : 4) : (kStreamWarps == 16 ? 1 : 2))
 w4a16_stream_kernel(const T* __restrict__ x, const uint16_t* __restrict__ qw, const T* __restrict__ scales,
                     const T* __restrict__ szeros, T* __restrict__ y, int M, int N, int K, int Kc, int S, int rpb, int seq,
-                    const __grid_constant__ StreamSmem L) {
+                    const __grid_constant__ StreamSmem L, const __grid_constant__ PeerArgs pa) {
   B200AWQ_STAMP(0);
   constexpr bool kBf16 = TypeTraits<T>::kIsBf16;
   constexpr int R = 8 * RO;  // output channels per CTA
+  constexpr int kStreamThreads = kStreamWarps * 32;
+  constexpr int kRoundK = kStreamWarps * kGroup;  // input channels consumed per round of the warps
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, tig = lane & 3;
   const int rank = (S > 1) ? (int)cluster_ctarank() : 0;
-  const int rb = (S > 1) ? (int)(blockIdx.x / S) : (int)blockIdx.x;
-  const int n0 = rb * R;
+  const int rb0 = ((S > 1) ? (int)(blockIdx.x / S) : (int)blockIdx.x) * L.rbs;  // first row block of this CTA
+  const int rbs = min(L.rbs, N / R - rb0);                                      // (the last CTA may own fewer)
   const int kbase = rank * Kc;
   const int ngroups = L.ngroups, nrounds = L.nrounds, nbar = L.nbar;
   const int wrow = Kc * 2;       // bytes of one 4-row quad over this CTA's k range
@@ -119,24 +120,26 @@ w4a16_stream_kernel(const T* __restrict__ x, const uint16_t* __restrict__ qw, co
   float* cpart = reinterpret_cast<float*>(smem + L.cpart);  // [tt][16][8]
   float2* xsum = reinterpret_cast<float2*>(smem + L.xsum);  // [8 TT tok][group] {X, C}   (MODE 2)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
-  uint64_t* xbar = bars + nbar;
+  uint64_t* xbar = bars + L.rbs * nbar;
 
   // ---- weight prefetch: 2*RO quad rows x nbar pieces of (rpb * 1024 k = 2 rpb KB), k-major issue order
   if (tid == 0) {
-    for (int b = 0; b <= nbar; ++b) mbar_init(&bars[b], 1);
+    for (int b = 0; b <= L.rbs * nbar; ++b) mbar_init(&bars[b], 1);
     mbar_fence_init();
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     B200AWQ_STAMP(7);
     const int piece = rpb * kRoundK * 2;  // bytes per quad row per barrier
-    for (int b = 0; b < nbar; ++b) {
-      const int off = b * piece;
-      const int len = min(piece, wrow - off);
-      mbar_expect_tx(&bars[b], 2 * RO * len);
+    for (int rbi = 0; rbi < rbs; ++rbi)
+      for (int b = 0; b < nbar; ++b) {
+        const int off = b * piece;
+        const int len = min(piece, wrow - off);
+        mbar_expect_tx(&bars[rbi * nbar + b], 2 * RO * len);
 #pragma unroll
-      for (int qd = 0; qd < 2 * RO; ++qd)
-        bulk_g2s(wbuf + qd * wrow + off, reinterpret_cast<const uint8_t*>(qw + (size_t)(rb * 2 * RO + qd) * K + kbase) + off,
-                 len, &bars[b]);
-    }
+        for (int qd = 0; qd < 2 * RO; ++qd)
+          bulk_g2s(wbuf + (rbi * 2 * RO + qd) * wrow + off,
+                   reinterpret_cast<const uint8_t*>(qw + (size_t)((rb0 + rbi) * 2 * RO + qd) * K + kbase) + off, len,
+                   &bars[rbi * nbar + b]);
+      }
   }
   pdl_launch_dependents();
   B200AWQ_STAMP(1);
@@ -144,14 +147,17 @@ w4a16_stream_kernel(const T* __restrict__ x, const uint16_t* __restrict__ qw, co
   {
     constexpr int PPG = R / 8;  // 16-byte pieces per group per tensor
     const int pieces = ngroups * PPG;
-    const uint8_t* sg = reinterpret_cast<const uint8_t*>(scales) + ((size_t)(kbase / kGroup) * N + n0) * 2;
-    const uint8_t* zg = reinterpret_cast<const uint8_t*>(szeros) + ((size_t)(kbase / kGroup) * N + n0) * 2;
-    for (int i = tid; i < 2 * pieces; i += kStreamThreads) {
-      const int which = i >= pieces;
-      const int j = which ? i - pieces : i;
-      const int grp = j / PPG, pc = j - grp * PPG;
-      cp_async16(reinterpret_cast<uint8_t*>(which ? zbuf : sbuf) + (grp * PPG + pc) * 16,
-                 (which ? zg : sg) + (size_t)grp * N * 2 + pc * 16);
+    for (int rbi = 0; rbi < rbs; ++rbi) {
+      const size_t goff = ((size_t)(kbase / kGroup) * N + (size_t)(rb0 + rbi) * R) * 2;
+      const uint8_t* sg = reinterpret_cast<const uint8_t*>(scales) + goff;
+      const uint8_t* zg = reinterpret_cast<const uint8_t*>(szeros) + goff;
+      for (int i = tid; i < 2 * pieces; i += kStreamThreads) {
+        const int which = i >= pieces;
+        const int j = which ? i - pieces : i;
+        const int grp = j / PPG, pc = j - grp * PPG;
+        cp_async16(reinterpret_cast<uint8_t*>(which ? zbuf : sbuf) + ((rbi * ngroups + grp) * PPG + pc) * 16,
+                   (which ? zg : sg) + (size_t)grp * N * 2 + pc * 16);
+      }
     }
     if (MODE) {  // tokens M .. 8*TT-1 do not exist: their correction terms must read as zero
       for (int i = tid + M * ngroups; i < 8 * TT * ngroups; i += kStreamThreads) xsum[i] = make_float2(0.f, 0.f);
@@ -211,12 +217,14 @@ w4a16_stream_kernel(const T* __restrict__ x, const uint16_t* __restrict__ qw, co
   }
   B200AWQ_STAMP(4);
 
+  const float zero4[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int rbi = 0; rbi < rbs; ++rbi) {  // row blocks of this CTA: weights of all of them were prefetched above
+  const int n0 = (rb0 + rbi) * R;
   float acc[TT][4];
 #pragma unroll
   for (int t = 0; t < TT; ++t)
 #pragma unroll
     for (int i = 0; i < 4; ++i) acc[t][i] = 0.f;
-  const float zero4[4] = {0.f, 0.f, 0.f, 0.f};
 
   // per-lane walking pointers; lanes whose token does not exist feed zeros
   const uint8_t* xp[TT];
@@ -227,9 +235,9 @@ w4a16_stream_kernel(const T* __restrict__ x, const uint16_t* __restrict__ qw, co
     live[t] = tok < M;
     xp[t] = xbuf + (live[t] ? tok : 0) * xrow + (warp * kGroup + tig * 32) * 2;
   }
-  const uint8_t* wp = wbuf + (g >> 2) * wrow + (warp * 2 + (tig >> 1)) * 128 + (g & 3) * 32 + (tig & 1) * 16;
-  const uint16_t* sq = sbuf + warp * R + g;
-  const uint16_t* zq = zbuf + warp * R + g;
+  const uint8_t* wp = wbuf + (rbi * 2 * RO + (g >> 2)) * wrow + (warp * 2 + (tig >> 1)) * 128 + (g & 3) * 32 + (tig & 1) * 16;
+  const uint16_t* sq = sbuf + (rbi * ngroups + warp) * R + g;
+  const uint16_t* zq = zbuf + (rbi * ngroups + warp) * R + g;
   const float2* sump = xsum + (2 * tig) * ngroups + warp;  // token 2 tig (+ 8 t), this warp's first group
   uint4 xq[TT][4];
 #pragma unroll
@@ -237,7 +245,7 @@ w4a16_stream_kernel(const T* __restrict__ x, const uint16_t* __restrict__ qw, co
 #pragma unroll
     for (int j = 0; j < 4; ++j) xq[t][j] = make_uint4(0, 0, 0, 0);
 
-  for (int rnd = 0, G = warp, left = 0, bar = 0; rnd < nrounds; ++rnd, G += kStreamWarps) {
+  for (int rnd = 0, G = warp, left = 0, bar = rbi * nbar; rnd < nrounds; ++rnd, G += kStreamWarps) {
     if (left == 0) {
       mbar_wait(&bars[bar++], 0);
       left = rpb;
@@ -341,7 +349,10 @@ w4a16_stream_kernel(const T* __restrict__ x, const uint16_t* __restrict__ qw, co
     for (int w = 0; w < kStreamWarps; ++w) v += red[w * TT * 128 + e];
     if (S == 1) {
       const int t = e >> 7, row = (e >> 3) & 15, tok = 8 * t + (e & 7);
-      if (tok < M && row < R) y[(size_t)tok * N + n0 + row] = from_float<T>(v);
+      if (tok < M && row < R) {
+        if (pa.world > 1) cpart[e] = v;  // exchanged with the peer GPUs below
+        else y[(size_t)tok * N + n0 + row] = from_float<T>(v);
+      }
     } else {
       cpart[e] = v;
     }
@@ -359,12 +370,64 @@ w4a16_stream_kernel(const T* __restrict__ x, const uint16_t* __restrict__ qw, co
           float v = 0.f;
 #pragma unroll
           for (int r = 0; r < 8; ++r) v += pv[r];
-          y[(size_t)tok * N + n0 + row] = from_float<T>(v);
+          if (pa.world > 1) cpart[e] = v;  // only this thread reads / writes the leader's own cpart[e]
+          else y[(size_t)tok * N + n0 + row] = from_float<T>(v);
         }
       }
     }
     cluster_sync_all();  // keep every CTA's shared memory alive until the leader has read it
   }
+  if (pa.world > 1 && rank == 0) {  // the CTA that holds the final sums of this row block (cluster leader if k is split)
+    // ---- row-parallel all-reduce fused into the epilogue (one-shot over NVLink peer memory):
+    // every rank writes its fp32 partials of this row block into EVERY rank's exchange buffer, raises a
+    // flag per destination, waits for the flags of all sources and sums the partials in rank order (so all
+    // ranks produce bit-identical outputs).  Epochs are per row block and live in device memory, which
+    // keeps the protocol valid under CUDA-graph replay; regions alternate with the epoch parity.
+    __shared__ unsigned int s_ep;
+    const int idx = n0 >> 3;
+    if (tid == 0) s_ep = pa.epoch[idx] + 1u;
+    __syncthreads();
+    const unsigned int ep = s_ep;
+    const int W = pa.world;
+    const size_t region = (size_t)((ep & 1u) * W + pa.rank) * pa.cap;
+    for (int e = tid; e < TT * 128; e += kStreamThreads) {
+      const int t = e >> 7, row = (e >> 3) & 15, tok = 8 * t + (e & 7);
+      if (tok < M && row < R) {
+        const float v = cpart[e];
+        const size_t off = region + (size_t)tok * N + n0 + row;
+        for (int r = 0; r < W; ++r)
+          if (!(pa.dbg & 2) || r == pa.rank) pa.data[r][off] = v;
+      }
+    }
+    if (!(pa.dbg & 4)) __threadfence_system();
+    __syncthreads();
+    if (tid < W) {
+      unsigned int* dst = pa.flags[tid] + (size_t)((ep & 1u) * W + pa.rank) * pa.cap_flags + idx;
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(ep) : "memory");
+      const unsigned int* src = pa.flags[pa.rank] + (size_t)((ep & 1u) * W + tid) * pa.cap_flags + idx;
+      unsigned int seen;
+      do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(src) : "memory");
+      } while ((int)(seen - ep) < 0 && !(pa.dbg & 1));
+    }
+    __syncthreads();
+    for (int e = tid; e < TT * 128; e += kStreamThreads) {
+      const int t = e >> 7, row = (e >> 3) & 15, tok = 8 * t + (e & 7);
+      if (tok < M && row < R) {
+        float v = 0.f;
+        for (int r = 0; r < W; ++r) {
+          const float* srcp = pa.data[pa.rank] + (size_t)((ep & 1u) * W + r) * pa.cap + (size_t)tok * N + n0 + row;
+          float pv;
+          asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(pv) : "l"(srcp) : "memory");
+          v += pv;
+        }
+        y[(size_t)tok * N + n0 + row] = from_float<T>(v);
+      }
+    }
+    if (tid == 0) pa.epoch[idx] = ep;
+  }
+  if (rbi + 1 < rbs) __syncthreads();  // `red` / `cpart` are reused by the next row block
+  }  // rbi
   B200AWQ_STAMP(6);
 }
 
@@ -377,6 +440,7 @@ extern "C" int b200awq_debug_read_trace(unsigned long long* host, int count) {
 // ------------------------------------------------------------------------------------ host
 constexpr int kStreamSmemCap = 200 * 1024;
 
+int g_stream_rbs = 0;  // row blocks per CTA: 0 = heuristic (tuning knob B200AWQ_STREAM_RBS)
 int g_stream_pad = 0;  // extra dynamic shared memory per CTA: limits co-residency (tuning knob B200AWQ_STREAM_PAD)
 
 static int next_seq() {
@@ -399,13 +463,24 @@ static int pick_splits(int K, int kc_target, int kc_env) {
   return best;
 }
 
-template <typename T, int RO, int TT, int MODE>
-static int launch_stream_t(const void* x, const void* qw, const void* sc, const void* sz, void* y, int M, int N, int K,
-                           int S, int rpb, bool pdl, cudaStream_t stream) {
+template <typename T, int RO, int TT, int MODE, int kStreamWarps>
+static int launch_stream_w(const void* x, const void* qw, const void* sc, const void* sz, void* y, int M, int N, int K,
+                           int S, int rpb, bool pdl, cudaStream_t stream, const PeerArgs* peers) {
   const int Kc = K / S;
-  const StreamSmem L = stream_smem_layout(RO, TT, MODE, M, Kc, rpb);
+  PeerArgs pa{};
+  if (peers) pa = *peers;
+  if (pa.world > 1 && TT != 1) return B200AWQ_ERR_SHAPE;
+  // several row blocks per CTA (all weight slices prefetched up front, activations / group sums staged once) is a
+  // tuning knob only: fat long-lived CTAs keep the NEXT launch's CTAs from becoming resident, which costs more
+  // than the saved prologues (measured, profiles/README.md)
+  const int nblk = N / (8 * RO);
+  int rbs = (g_stream_rbs > 0) ? g_stream_rbs : 1;
+  if (S != 1 || rbs > nblk) rbs = 1;
+  StreamSmem L = stream_smem_layout(RO, TT, MODE, M, Kc, rpb, rbs, kStreamWarps);
+  if (L.total > kStreamSmemCap && rbs > 1) rbs = 1, L = stream_smem_layout(RO, TT, MODE, M, Kc, rpb, 1, kStreamWarps);
   if (L.total > kStreamSmemCap) return B200AWQ_ERR_SHAPE;
-  auto kern = w4a16_stream_kernel<T, RO, TT, MODE>;
+  constexpr int kStreamThreads = kStreamWarps * 32;
+  auto kern = w4a16_stream_kernel<T, RO, TT, MODE, kStreamWarps>;
   static bool attr_set = false;  // per instantiation
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemCap);
@@ -413,12 +488,12 @@ static int launch_stream_t(const void* x, const void* qw, const void* sc, const 
     attr_set = true;
   }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(N / (8 * RO)) * S);
+  cfg.gridDim = dim3((unsigned)((nblk + rbs - 1) / rbs) * S);
   cfg.blockDim = dim3(kStreamThreads);
   // Co-residency: a launch that fits in one wave runs fastest with FEW CTAs per SM (the next launch's
   // CTAs only need enough room to prefetch); multi-wave launches want as many as fit (measured).
   size_t dyn = L.total;
-  const int ctas = (N / (8 * RO)) * S;
+  const int ctas = ((nblk + rbs - 1) / rbs) * S;
   const int per_sm = ctas <= 2 * 148 ? 2 : (ctas <= 3 * 148 ? 3 : 0);
   if (g_stream_pad > 0)
     dyn += (size_t)g_stream_pad;
@@ -444,37 +519,52 @@ static int launch_stream_t(const void* x, const void* qw, const void* sc, const 
   cfg.attrs = attrs;
   cfg.numAttrs = na;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, (const T*)x, (const uint16_t*)qw, (const T*)sc, (const T*)sz, (T*)y, M, N,
-                                     K, Kc, S, rpb, next_seq(), L);
+                                     K, Kc, S, rpb, next_seq(), L, pa);
   return e == cudaSuccess ? 0 : (int)e;
+}
+
+int g_stream_warps = 0;  // 0 = heuristic, 8 or 16 (tuning knob B200AWQ_STREAM_WARPS)
+
+template <typename T, int RO, int TT, int MODE>
+static int launch_stream_t(const void* x, const void* qw, const void* sc, const void* sz, void* y, int M, int N, int K,
+                           int S, int rpb, bool pdl, cudaStream_t stream, const PeerArgs* peers) {
+  // 8 warps per CTA by default; 16 (shorter serial chain after griddepcontrol.wait, half the co-residency) is a knob
+  const int ctas = (N / (8 * RO)) * S;
+  (void)ctas;
+  const int w = g_stream_warps ? g_stream_warps : 8;  // measured (profiles/): 16 warps or several row blocks per CTA do not pay
+  if (w == 16) return launch_stream_w<T, RO, TT, MODE, 16>(x, qw, sc, sz, y, M, N, K, S, rpb, pdl, stream, peers);
+  return launch_stream_w<T, RO, TT, MODE, 8>(x, qw, sc, sz, y, M, N, K, S, rpb, pdl, stream, peers);
 }
 
 template <typename T, int MODE>
 static int launch_stream_m(const void* x, const void* qw, const void* sc, const void* sz, void* y, int M, int N, int K,
-                           int S, int ro, int rpb, bool pdl, cudaStream_t stream) {
+                           int S, int ro, int rpb, bool pdl, cudaStream_t stream, const PeerArgs* peers) {
   if (M <= 8) {
-    if (ro == 2) return launch_stream_t<T, 2, 1, MODE>(x, qw, sc, sz, y, M, N, K, S, rpb, pdl, stream);
-    return launch_stream_t<T, 1, 1, MODE>(x, qw, sc, sz, y, M, N, K, S, rpb, pdl, stream);
+    if (ro == 2) return launch_stream_t<T, 2, 1, MODE>(x, qw, sc, sz, y, M, N, K, S, rpb, pdl, stream, peers);
+    return launch_stream_t<T, 1, 1, MODE>(x, qw, sc, sz, y, M, N, K, S, rpb, pdl, stream, peers);
   }
-  if (ro == 2) return launch_stream_t<T, 2, 2, MODE>(x, qw, sc, sz, y, M, N, K, S, rpb, pdl, stream);
-  return launch_stream_t<T, 1, 2, MODE>(x, qw, sc, sz, y, M, N, K, S, rpb, pdl, stream);
+  if (ro == 2) return launch_stream_t<T, 2, 2, MODE>(x, qw, sc, sz, y, M, N, K, S, rpb, pdl, stream, peers);
+  return launch_stream_t<T, 1, 2, MODE>(x, qw, sc, sz, y, M, N, K, S, rpb, pdl, stream, peers);
 }
 
 int launch_stream(const void* x, const void* qw, const void* sc, const void* sz, void* y, int M, int N, int K, int dtype,
-                  bool pdl, const StreamTuning& tune, cudaStream_t stream) {
+                  bool pdl, const StreamTuning& tune, cudaStream_t stream, const PeerArgs* peers) {
   if (M < 1 || M > 16 || N % 8 || K % kGroup) return B200AWQ_ERR_SHAPE;
   const int ro = (N % 16 == 0) ? 2 : 1;
   const int kc_target = M <= 2 ? 4096 : (M <= 8 ? 2048 : 1024);
   const int S = pick_splits(K, kc_target, tune.kc);
   const int rpb = tune.rpb > 0 ? tune.rpb : 64;  // default: one barrier (4 large copies) per CTA
+  g_stream_rbs = tune.rbs;
+  g_stream_warps = (tune.warps == 8 || tune.warps == 16) ? tune.warps : 0;
   g_stream_pad = tune.pad;  // > 0: explicit extra bytes, 0: heuristic, < 0: none
   // default arithmetic: fp16 -> group-factored (MODE 2), bf16 -> operand-exact (MODE 0); see the header comment
   const int mode = (tune.mode == 0 || tune.mode == 2) ? tune.mode : (dtype == B200AWQ_DTYPE_F16 ? 2 : 0);
   if (dtype == B200AWQ_DTYPE_F16) {
-    if (mode == 0) return launch_stream_m<__half, 0>(x, qw, sc, sz, y, M, N, K, S, ro, rpb, pdl, stream);
-    return launch_stream_m<__half, 2>(x, qw, sc, sz, y, M, N, K, S, ro, rpb, pdl, stream);
+    if (mode == 0) return launch_stream_m<__half, 0>(x, qw, sc, sz, y, M, N, K, S, ro, rpb, pdl, stream, peers);
+    return launch_stream_m<__half, 2>(x, qw, sc, sz, y, M, N, K, S, ro, rpb, pdl, stream, peers);
   }
-  if (mode == 0) return launch_stream_m<__nv_bfloat16, 0>(x, qw, sc, sz, y, M, N, K, S, ro, rpb, pdl, stream);
-  return launch_stream_m<__nv_bfloat16, 2>(x, qw, sc, sz, y, M, N, K, S, ro, rpb, pdl, stream);
+  if (mode == 0) return launch_stream_m<__nv_bfloat16, 0>(x, qw, sc, sz, y, M, N, K, S, ro, rpb, pdl, stream, peers);
+  return launch_stream_m<__nv_bfloat16, 2>(x, qw, sc, sz, y, M, N, K, S, ro, rpb, pdl, stream, peers);
 }
 
 }  // namespace b200awq

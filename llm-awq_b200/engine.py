@@ -29,6 +29,8 @@ def lib() -> ctypes.CDLL:
         L.gemv_forward_4bit.restype = ci
         L.gemm_forward_4bit.argtypes = L.b200awq_w4a16_gemm.argtypes
         L.gemm_forward_4bit.restype = ci
+        L.b200awq_w4a16_gemv_allreduce.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp, vp]
+        L.b200awq_w4a16_gemv_allreduce.restype = ci
         L.b200awq_w4a16_gemm_workspace_bytes.argtypes = [ci, ci, ci]
         L.b200awq_w4a16_gemm_workspace_bytes.restype = sz
         L.b200awq_set_pdl.argtypes = [ci]

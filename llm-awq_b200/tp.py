@@ -104,3 +104,72 @@ class RowParallelWQLinear(nn.Module):
         if self.world > 1:
             torch.distributed.all_reduce(y, op=torch.distributed.ReduceOp.SUM, group=self.group)
         return y + self.bias if self.bias is not None else y
+
+
+class PeerExchange:
+    """Symmetric (peer-mapped over NVLink) buffers for the fused GEMV + all-reduce kernel
+    (`b200awq_w4a16_gemv_allreduce`, include/b200awq.h).  One instance can serve every row-parallel layer
+    of a model: all ranks must issue the same sequence of calls.  Allocation uses
+    torch.distributed._symmetric_memory (CUDA VMM peer mappings); plumbing only, no kernels."""
+
+    def __init__(self, max_tokens, max_out_features, group=None):
+        import ctypes
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        group = group or dist.group.WORLD
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        if self.world > 8:
+            raise ValueError("the fused exchange supports at most 8 ranks")
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.cap_floats = max_tokens * max_out_features
+        self.cap_flags = max_out_features // 8
+        self.data = symm_mem.empty(2 * self.world * self.cap_floats, dtype=torch.float32, device=dev)
+        self.flags = symm_mem.empty(2 * self.world * self.cap_flags, dtype=torch.int32, device=dev)
+        self.flags.zero_()
+        self.epoch = torch.zeros(self.cap_flags, dtype=torch.int32, device=dev)
+        hd = symm_mem.rendezvous(self.data, group.group_name)
+        hf = symm_mem.rendezvous(self.flags, group.group_name)
+        torch.cuda.synchronize()
+        dist.barrier(group)          # every rank's flags are zero before anybody's first call
+
+        class _Peers(ctypes.Structure):
+            _fields_ = [("data", ctypes.c_void_p * 8), ("flags", ctypes.c_void_p * 8), ("epoch", ctypes.c_void_p),
+                        ("rank", ctypes.c_int), ("world", ctypes.c_int), ("cap_floats", ctypes.c_int),
+                        ("cap_flags", ctypes.c_int)]
+        p = _Peers()
+        for r in range(self.world):
+            p.data[r] = int(hd.buffer_ptrs[r])
+            p.flags[r] = int(hf.buffer_ptrs[r])
+        p.epoch = self.epoch.data_ptr()
+        p.rank, p.world, p.cap_floats, p.cap_flags = self.rank, self.world, self.cap_floats, self.cap_flags
+        self._struct, self._handles = p, (hd, hf)
+        self.ptr = ctypes.cast(ctypes.pointer(p), ctypes.c_void_p)
+
+
+class FusedRowParallelWQLinear(RowParallelWQLinear):
+    """Row-parallel layer whose decode path (tokens <= 8) is ONE kernel: local GEMV + the sum over ranks
+    through NVLink peer memory.  Larger token counts use the local kernel + one NCCL all-reduce."""
+
+    def __init__(self, full: WQLinear, rank, world, exchange: PeerExchange, group=None):
+        super().__init__(full, rank, world, group)
+        self.exchange = exchange
+
+    def forward(self, x_local):
+        import ctypes
+        from .engine import lib
+        m = x_local.numel() // x_local.shape[-1]
+        loc = self.local
+        if self.world == 1 or m > 8 or m * loc.out_features > self.exchange.cap_floats:
+            return super().forward(x_local)
+        x = x_local if x_local.is_contiguous() else x_local.contiguous()
+        y = torch.empty(*x.shape[:-1], loc.out_features, dtype=x.dtype, device=x.device)
+        p = lambda t: ctypes.c_void_p(t.data_ptr())
+        rc = lib().b200awq_w4a16_gemv_allreduce(p(x), p(loc.qweight), p(loc.scales), p(loc.scaled_zeros), p(y), m,
+                                                loc.out_features, loc.in_features, loc.group_size,
+                                                0 if x.dtype == torch.float16 else 1, self.exchange.ptr,
+                                                ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        if rc == -1:                       # shape outside the fused envelope: local kernel + NCCL
+            return super().forward(x_local)
+        if rc != 0:
+            raise RuntimeError(lib().b200awq_strerror(rc).decode())
+        return y + self.bias if self.bias is not None else y

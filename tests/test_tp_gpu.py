@@ -31,12 +31,31 @@ def _worker(rank, world, port, out_dir):
     col = tp.ColumnParallelWQLinear(up, rank, world).to(dev)
     row = tp.RowParallelWQLinear(down, rank, world).to(dev)
     row.bias = row.bias.to(dev)
+    ex = tp.PeerExchange(8, hidden)
+    fused = tp.FusedRowParallelWQLinear(down, rank, world, ex).to(dev)
+    fused.bias = fused.bias.to(dev)
     outs = {}
     for M in (1, 5, 33):
         x = gen_x(M, hidden, seed=M).to(dev)
         h = col(x)                 # [M, inter / world] on this rank
         y = row(h)                 # local kernel + ONE all-reduce + bias
-        outs[M] = (h.cpu(), y.cpu())
+        yf = [fused(h).cpu() for _ in range(3)]      # fused GEMV + NVLink exchange (M <= 8), repeated (epochs)
+        outs[M] = (h.cpu(), y.cpu(), yf)
+    # CUDA-graph replay of the fused kernel (epochs live on the device)
+    hs = col(gen_x(2, hidden, seed=2).to(dev)).clone()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        fused(hs)
+    s.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        yg = fused(hs)
+    reps = []
+    for _ in range(4):
+        g.replay()
+        torch.cuda.synchronize()
+        reps.append(yg.cpu().clone())
+    outs["graph"] = (reps, row(hs).cpu())
     torch.save(outs, os.path.join(out_dir, f"r{rank}.pt"))
     dist.barrier()
     dist.destroy_process_group()
@@ -62,3 +81,11 @@ def test_column_then_row_parallel_on_kernels_nccl(tmp_path):
         for r in range(world):
             assert torch.equal(outs[r][M][1], outs[0][M][1])                   # all ranks hold the reduced result
         assert rel_err(np64(outs[0][M][1]), y64) < 2e-3                        # two fp16 roundings (partials, bias add)
+        for yf in outs[0][M][2]:                                                # fused path: fp32 partials, one rounding
+            assert rel_err(np64(yf), y64) < 1e-3
+        for r in range(world):
+            for a, b in zip(outs[r][M][2], outs[0][M][2]):
+                assert torch.equal(a, b)                                        # bit-identical across ranks and repeats
+    reps, ref = outs[0]["graph"]
+    for rr in reps:
+        assert torch.equal(rr, reps[0]) and rel_err(np64(rr), np64(ref)) < 1e-3

@@ -77,6 +77,7 @@ b200awq::UmmaTuning umma_tuning() {
   b200awq::UmmaTuning t;
   t.tn = env_int("B200AWQ_UMMA_TN", 0);
   t.max_ctas = env_int("B200AWQ_UMMA_CTAS", 0);
+  t.split = env_int("B200AWQ_UMMA_SPLIT", 0);
   return t;
 }
 

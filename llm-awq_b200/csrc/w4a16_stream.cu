@@ -162,9 +162,8 @@ w4a16_stream_kernel(const T* __restrict__ x, const uint16_t* __restrict__ qw, co
     if (MODE) {  // tokens M .. 8*TT-1 do not exist: their correction terms must read as zero
       for (int i = tid + M * ngroups; i < 8 * TT * ngroups; i += kStreamThreads) xsum[i] = make_float2(0.f, 0.f);
     }
-    cp_async_wait_all();
   }
-  __syncthreads();  // barrier inits, scales / zeros and the zeroed correction terms visible to everyone
+  __syncthreads();  // barrier inits and the zeroed correction terms visible to everyone
   B200AWQ_STAMP(2);
   pdl_wait_prior_grid();  // activations (and y) belong to the stream order from here on
   B200AWQ_STAMP(3);
@@ -215,6 +214,8 @@ w4a16_stream_kernel(const T* __restrict__ x, const uint16_t* __restrict__ qw, co
     }
     __syncwarp();
   }
+  cp_async_wait_all();  // scales / zeros (issued before the wait; their latency overlapped everything above)
+  __syncthreads();
   B200AWQ_STAMP(4);
 
   const float zero4[4] = {0.f, 0.f, 0.f, 0.f};

@@ -16,12 +16,17 @@
 //   * UMMA N = TN tokens (32..256).  The activation tile X[tok, 64 k] arrives by TMA
 //     with the 128-byte swizzle and is consumed in place as the K-major B operand.
 //   * D (128 lanes x TN fp32 columns) stays in TMEM for the whole K loop.
-// Warp roles (256 threads, persistent over output tiles):
+// Warp roles (384 threads, persistent over output tiles):
 //   warp 0 lane 0  TMA producer        (activation tile + packed-weight tile per stage)
 //   warp 1 lane 0  tcgen05.mma issuer  (4 x K16 per stage, commits release the stage)
 //   warp 2         TMEM allocation / release
-//   warps 4-7      dequantise -> TMEM  and, per tile, the epilogue
-//                  (tcgen05.ld -> cvt -> smem transpose -> coalesced 16-byte stores)
+//   warps 4-11     two groups of 4 (one warp per TMEM lane quarter each) that take alternate 64-k stages:
+//                  dequantise -> TMEM; per tile each group converts alternate 32-token chunks of the epilogue
+//                  (tcgen05.ld -> cvt -> smem transpose -> coalesced 16-byte stores).  With one group the kernel
+//                  was bound by the dequantisation latency of a single warp per scheduler (~800 cycles per
+//                  stage against 512 for the MMAs of a 256-token tile); see profiles/README.md.
+// Small token counts: the k range is split over a thread-block cluster (2/4/8 CTAs share a tile) and the fp32
+// partial tiles are reduced through distributed shared memory in the epilogue (mbarriers with cluster scope).
 #include <cuda.h>  // CUtensorMap (types only; the encoder is resolved at run time)
 
 #include "w4_common.cuh"
@@ -32,7 +37,7 @@ namespace b200awq {
 constexpr int kBM = 128;      // output channels per tile (TMEM lanes)
 constexpr int kBK = 64;       // k per pipeline stage
 constexpr int kAStages = 4;   // dequantised-A ring in TMEM (32 columns each)
-constexpr int kUmmaThreads = 256;
+constexpr int kUmmaThreads = 384;  // 4 service warps + 2 groups of 4 dequantisation / epilogue warps
 constexpr int kWBytes = kBM * kBK / 2;  // 4096: packed weights per stage
 
 // ---------------------------------------------------------------- tcgen05 / TMA PTX
@@ -94,6 +99,24 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
       : "r"(taddr)                                                                                                       \
       : "memory")
 
+// ---------------------------------------------------------------- cluster-scope mbarrier helpers (split-K)
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* local_bar, uint32_t rank) {
+  const uint32_t a = map_to_rank(smem_u32(local_bar), rank);
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+
 template <int TN>
 struct UmmaSmem {
   static constexpr int kXBytes = TN * 128;  // TN token rows x 64 k x 2 B
@@ -103,7 +126,9 @@ struct UmmaSmem {
   static constexpr int kStages = (200 * 1024 - kOutBytes - 1024) / kStageBytes >= 8
                                      ? 8
                                      : (200 * 1024 - kOutBytes - 1024) / kStageBytes;
+  static constexpr int kPartBytes = TN <= 64 ? TN * kBM * 4 : 0;  // fp32 partial tile for split-K (TN <= 64 only)
   static constexpr int kTotal = kStages * kStageBytes + kOutBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kTotalSplit = kTotal + kPartBytes;
   static constexpr int kTmemCols = (TN + 32 * kAStages) <= 64    ? 64
                                    : (TN + 32 * kAStages) <= 128 ? 128
                                    : (TN + 32 * kAStages) <= 256 ? 256
@@ -113,7 +138,7 @@ struct UmmaSmem {
 template <typename T, int TN>
 __global__ void __launch_bounds__(kUmmaThreads, 1)
 w4a16_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
-                  const T* __restrict__ scales, const T* __restrict__ szeros, T* __restrict__ y, int M, int N, int K) {
+                  const T* __restrict__ scales, const T* __restrict__ szeros, T* __restrict__ y, int M, int N, int K, int S) {
   using L = UmmaSmem<TN>;
   constexpr int STAGES = L::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -128,12 +153,20 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   uint64_t* aempty = afull + kAStages;    // [kAStages] MMA commit -> dequant
   uint64_t* dfull = aempty + kAStages;    // MMA commit -> epilogue
   uint64_t* dempty = dfull + 1;           // epilogue (4) -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(dempty + 1);
+  uint64_t* pfull = dempty + 1;           // split-K: every rank's partial tile is written   (4 S remote arrivals)
+  uint64_t* pempty = pfull + 1;           // split-K: every rank has finished reading MY tile (4 S remote arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pempty + 1);
+  float* pbuf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);  // [TN][128] fp32 (S > 1 only)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_kb = K / kBK;
   const int tok_tiles = (M + TN - 1) / TN;
   const int num_tiles = tok_tiles * (N / kBM);
+  // split-K over a thread-block cluster: rank r of S owns k blocks [kb0, kb0 + num_kb); the cluster walks tiles together
+  const int crank = (S > 1) ? (int)cluster_ctarank() : 0;
+  const int num_kb = K / kBK / S;
+  const int kb0 = crank * num_kb;
+  const int tile0 = (S > 1) ? (int)(blockIdx.x / S) : (int)blockIdx.x;
+  const int tile_step = (S > 1) ? (int)(gridDim.x / S) : (int)gridDim.x;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) {
@@ -145,7 +178,9 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       mbar_init(&aempty[i], 1);
     }
     mbar_init(dfull, 1);
-    mbar_init(dempty, 4);
+    mbar_init(dempty, 8);
+    mbar_init(pfull, 4 * S);
+    mbar_init(pempty, 4 * S);
     mbar_fence_init();
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     tma_prefetch_desc(&tm_x);
@@ -159,6 +194,7 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
+  if (S > 1) cluster_sync_all();  // remote mbarrier arrivals must not race the inits
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t d_tmem = tmem_base;             // columns [0, TN)
@@ -172,13 +208,13 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       pdl_wait_prior_grid();  // activations come from the previous kernel in the stream
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         const int oc_tile = tile / tok_tiles, tok_tile = tile % tok_tiles;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[s], ph ^ 1);
           mbar_expect_tx(&full[s], L::kStageBytes);
-          tma_load_2d(xs + s * L::kXBytes, &tm_x, &full[s], kb * kBK, tok_tile * TN);
-          tma_load_2d(ws + s * kWBytes, &tm_w, &full[s], kb * kBK, oc_tile * (kBM / 4));
+          tma_load_2d(xs + s * L::kXBytes, &tm_x, &full[s], (kb0 + kb) * kBK, tok_tile * TN);
+          tma_load_2d(ws + s * kWBytes, &tm_w, &full[s], (kb0 + kb) * kBK, oc_tile * (kBM / 4));
           if (++s == STAGES) {
             s = 0;
             ph ^= 1;
@@ -194,7 +230,7 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       constexpr uint32_t idesc = (1u << 4) | (kFmt << 7) | (kFmt << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
       int s = 0, as = 0;
       uint32_t ph = 0, aph = 0, dph = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < num_tiles; tile += tile_step) {
         mbar_wait(dempty, dph ^ 1);  // accumulator drained by the epilogue of the previous tile
         tc_fence_after();
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -227,24 +263,28 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     const int q = warp & 3;             // TMEM lane quarter this warp may touch
     const int row = q * 32 + lane;      // output channel inside the tile == TMEM lane
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    const int et = (warp - 4) * 32 + lane;  // 0..127
+    const int grp = (warp - 4) >> 2;               // the two groups take alternate 64-k stages and alternate epilogue chunks
+    const int et = ((warp - 4) & 3) * 32 + lane;  // 0..127 inside the group
     int s = 0, as = 0;
-    uint32_t ph = 0, aph = 0, dph = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    uint32_t ph = 0, aph = 0, dph = 0, pph = 0;
+    for (int tile = tile0; tile < num_tiles; tile += tile_step) {
       const int oc_tile = tile / tok_tiles, tok_tile = tile % tok_tiles;
       const int n = oc_tile * kBM + row;
-      const uint16_t* sp = reinterpret_cast<const uint16_t*>(scales) + n;
-      const uint16_t* zp = reinterpret_cast<const uint16_t*>(szeros) + n;
+      const uint16_t* sp = reinterpret_cast<const uint16_t*>(scales) + (size_t)(kb0 / 2) * N + n;
+      const uint16_t* zp = reinterpret_cast<const uint16_t*>(szeros) + (size_t)(kb0 / 2) * N + n;
       uint16_t s_nxt = __ldg(sp), z_nxt = __ldg(zp);
       uint32_t s2 = 0, z2 = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
-        if ((kb & 1) == 0) {  // a 128-k group spans two stages
-          s2 = splat16(s_nxt);
-          z2 = splat16(z_nxt);
-          if (kb + 2 < num_kb) {
-            s_nxt = __ldg(sp + (size_t)(kb / 2 + 1) * N);
-            z_nxt = __ldg(zp + (size_t)(kb / 2 + 1) * N);
-          }
+        if ((kb & 1) != grp) {  // the other group's stage (num_kb is even: a 128-k group is one stage of each)
+          if (++s == STAGES) s = 0, ph ^= 1;
+          if (++as == kAStages) as = 0, aph ^= 1;
+          continue;
+        }
+        s2 = splat16(s_nxt);
+        z2 = splat16(z_nxt);
+        if (kb + 2 < num_kb) {
+          s_nxt = __ldg(sp + (size_t)(kb / 2 + 1) * N);
+          z_nxt = __ldg(zp + (size_t)(kb / 2 + 1) * N);
         }
         mbar_wait(&full[s], ph);
         const uint8_t* wp = ws + s * kWBytes + (row >> 2) * 128 + (row & 3) * 32;
@@ -286,19 +326,61 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       mbar_wait(dfull, dph);
       dph ^= 1;
       tc_fence_after();
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // staging buffers of the previous tile are fully read
+      if (S > 1 && grp == 1) {  // the partial-tile exchange is done by group 0 alone
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dempty);
+        continue;
+      }
+      if (S > 1) {
+        // split-K: fp32 partial tile -> own shared memory; every rank then reduces TN / S tokens of the tile
+        // over distributed shared memory and stores them (no atomics, fixed summation order)
+        if constexpr (TN <= 64) {
+          mbar_wait_cluster(pempty, pph ^ 1);  // all ranks have finished reading my previous partial tile
 #pragma unroll 1
-      for (int c = 0; c < TN / 32; ++c) {
+          for (int c = 0; c < TN / 32; ++c) {
+            uint32_t v[32];
+            B200AWQ_TMEM_LD32(d_tmem + lane_base + c * 32, v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 32; ++j) pbuf[(c * 32 + j) * kBM + row] = __uint_as_float(v[j]);
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(dempty);  // the accumulator may be overwritten by the next tile
+            for (int r = 0; r < S; ++r) mbar_arrive_remote(pfull, (uint32_t)r);
+          }
+          mbar_wait_cluster(pfull, pph);  // every rank's partial tile is in its shared memory
+          const int tpr = TN / S;
+          const uint32_t base = smem_u32(pbuf);
+          for (int t = crank * tpr; t < (crank + 1) * tpr; ++t) {
+            const int tok = tok_tile * TN + t;
+            if (tok >= M) break;
+            float acc = 0.f;
+            for (int r = 0; r < S; ++r) acc += ld_cluster_f32(map_to_rank(base + (uint32_t)(t * kBM + et) * 4u, (uint32_t)r));
+            y[(size_t)tok * N + oc_tile * kBM + et] = from_float<T>(acc);
+          }
+          __syncwarp();
+          if (lane == 0)
+            for (int r = 0; r < S; ++r) mbar_arrive_remote(pempty, (uint32_t)r);
+          pph ^= 1;
+        }
+        continue;
+      }
+      // each group converts its own 32-token chunks (c & 1 == grp) through its own staging buffer
+      uint8_t* ob = outb + grp * 32 * L::kOutRow;
+#pragma unroll 1
+      for (int c = grp; c < TN / 32; c += 2) {
         const int tok0 = tok_tile * TN + c * 32;
-        if (tok0 >= M) break;  // uniform across the CTA
+        if (tok0 >= M) break;  // uniform across the group
         uint32_t v[32];
         B200AWQ_TMEM_LD32(d_tmem + lane_base + c * 32, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        uint8_t* ob = outb + (c & 1) * 32 * L::kOutRow;
 #pragma unroll
         for (int j = 0; j < 32; ++j)
           *reinterpret_cast<T*>(ob + j * L::kOutRow + row * 2) = from_float<T>(__uint_as_float(v[j]));
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int rr = (et >> 4) + 8 * i, cc = et & 15;
@@ -307,13 +389,17 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             *reinterpret_cast<uint4*>(y + (size_t)(tok0 + rr) * N + oc_tile * kBM + cc * 8) = val;
           }
         }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");  // buffer free for this group's next chunk
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(dempty);
     }
+    if (S > 1 && grp == 0) mbar_wait_cluster(pempty, pph ^ 1);  // nobody is still reading my last partial tile
   }
 
+  __syncwarp();
+  if (S > 1) cluster_sync_all();  // no CTA of the cluster exits while a peer may still touch its shared memory / barriers
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
@@ -355,7 +441,7 @@ static int sm_count() {
 
 template <typename T, int TN>
 static int launch_umma_t(const void* x, const void* qw, const void* sc, const void* sz, void* y, int M, int N, int K,
-                         bool pdl, int max_ctas, cudaStream_t stream) {
+                         bool pdl, int max_ctas, int split, cudaStream_t stream) {
   using L = UmmaSmem<TN>;
   EncodeTiledFn enc = get_encoder();
   if (!enc) return B200AWQ_ERR_DRIVER;
@@ -383,21 +469,33 @@ static int launch_umma_t(const void* x, const void* qw, const void* sc, const vo
   auto kern = w4a16_umma_kernel<T, TN>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotalSplit);
     if (e != cudaSuccess) return (int)e;
     attr_set = true;
   }
   const int tiles = ((M + TN - 1) / TN) * (N / kBM);
-  int ctas = sm_count();
-  if (max_ctas > 0 && max_ctas < ctas) ctas = max_ctas;
-  if (tiles < ctas) ctas = tiles;
+  int sms = sm_count();
+  if (max_ctas > 0 && max_ctas < sms) sms = max_ctas;
+  // split-K over a cluster when the tiles alone cannot fill the machine (small token counts): S ranks share a tile,
+  // each walks K / S and the partial tiles are reduced through distributed shared memory in the epilogue
+  int S = 1;
+  if (TN <= 64 && split > 1 && split <= 8 && (split & (split - 1)) == 0 && (K / kGroup) % split == 0) S = split;
+  int clusters = sms / S;
+  if (tiles < clusters) clusters = tiles;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)ctas);
+  cfg.gridDim = dim3((unsigned)(clusters * S));
   cfg.blockDim = dim3(kUmmaThreads);
-  cfg.dynamicSmemBytes = L::kTotal;
+  cfg.dynamicSmemBytes = S > 1 ? L::kTotalSplit : L::kTotal;
   cfg.stream = stream;
-  cudaLaunchAttribute attrs[1];
+  cudaLaunchAttribute attrs[2];
   int na = 0;
+  if (S > 1) {
+    attrs[na].id = cudaLaunchAttributeClusterDimension;
+    attrs[na].val.clusterDim.x = S;
+    attrs[na].val.clusterDim.y = 1;
+    attrs[na].val.clusterDim.z = 1;
+    ++na;
+  }
   if (pdl) {
     attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attrs[na].val.programmaticStreamSerializationAllowed = 1;
@@ -405,7 +503,7 @@ static int launch_umma_t(const void* x, const void* qw, const void* sc, const vo
   }
   cfg.attrs = attrs;
   cfg.numAttrs = na;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tm_x, tm_w, (const T*)sc, (const T*)sz, (T*)y, M, N, K);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tm_x, tm_w, (const T*)sc, (const T*)sz, (T*)y, M, N, K, S);
   return e == cudaSuccess ? 0 : (int)e;
 }
 
@@ -413,9 +511,28 @@ int launch_umma(const void* x, const void* qw, const void* sc, const void* sz, v
                 bool pdl, const UmmaTuning& tune, cudaStream_t stream) {
   if (M < 1 || N % kBM || K % kGroup) return B200AWQ_ERR_SHAPE;
   int tn = tune.tn;
-  if (tn != 32 && tn != 64 && tn != 128 && tn != 256) tn = M <= 32 ? 32 : (M <= 64 ? 64 : (M <= 128 ? 128 : 256));
+  int split = tune.split;
+  if (tn != 32 && tn != 64 && tn != 128 && tn != 256) {
+    // joint choice of the token tile and the k split by a small cost model (cycles per CTA, measured constants):
+    // a 64-k stage costs max(dequantisation ~450, MMA 2*tn + 100) cycles, a tile's epilogue ~10*tn (+6000 when the
+    // partial tiles of a split have to be reduced over the cluster), a launch ~12000; makespan = waves x that
+    const int sms = sm_count();
+    long best = -1;
+    for (int c = 256; c >= 32; c >>= 1) {
+      if (c > 32 && c / 2 >= M) continue;
+      const int tiles = ((M + c - 1) / c) * (N / kBM);
+      for (int sp = 1; sp <= 8; sp *= 2) {
+        if (sp > 1 && (c > 64 || (K / kGroup) % sp || K / sp < 512 || tune.split == 1)) continue;
+        if (tune.split > 1 && sp != tune.split && c <= 64) continue;
+        const long per_tile = (long)(K / kBK / sp) * (2 * c + 100 > 450 ? 2 * c + 100 : 450) + 10 * c + (sp > 1 ? 6000 : 0);
+        const long slots = sms / sp;  // clusters that run at once
+        const long cost = 12000 + ((tiles + slots - 1) / slots) * per_tile;
+        if (best < 0 || cost < best) best = cost, tn = c, split = sp;
+      }
+    }
+  }
 #define B200AWQ_UMMA_CASE(TT, TN_) \
-  return launch_umma_t<TT, TN_>(x, qw, sc, sz, y, M, N, K, pdl, tune.max_ctas, stream)
+  return launch_umma_t<TT, TN_>(x, qw, sc, sz, y, M, N, K, pdl, tune.max_ctas, split, stream)
   if (dtype == B200AWQ_DTYPE_F16) {
     switch (tn) {
       case 32: B200AWQ_UMMA_CASE(__half, 32);

@@ -72,18 +72,16 @@ size_t b200awq_w4a16_gemm_workspace_bytes(int m, int n, int k);
  * GEMV of THIS rank's k-slice fused with the sum all-reduce of the [m, n] partial outputs over NVLink peer
  * memory, in one kernel.  Every rank calls it with its own shard and the same (m, n); on return (stream order)
  * y holds the full sum on every rank, bit-identical across ranks.
- *   data[r]   rank r's exchange buffer as mapped in this process (symmetric / peer-mapped allocation),
- *             fp32, >= 2 * world * cap_floats elements, any content
- *   flags[r]  rank r's flag words (uint32), >= 2 * world * cap_flags elements, ZERO before the first call
- *   epoch     this rank's private counters (device memory, uint32, >= cap_flags elements, ZERO before first use)
- *   cap_floats >= m * n, cap_flags >= n / 8.  1 <= m <= 8, world <= 8.  All ranks must issue the same
- *   sequence of calls on these buffers.  Safe under CUDA-graph capture / replay (no host-side state). */
+ *   data[r]   rank r's exchange buffer as mapped in this process (symmetric / peer-mapped allocation):
+ *             8-byte words {fp32 partial, epoch}, >= 2 * world * cap_words of them, ZERO before the first call
+ *   epoch     this rank's private counters (device memory, uint32, >= n_max / 8 elements, ZERO before first use)
+ *   cap_words >= m * n.  1 <= m <= 8, world <= 8.  All ranks must issue the same sequence of calls on these
+ *   buffers.  Safe under CUDA-graph capture / replay (no host-side state). */
 typedef struct b200awq_peers {
   void* data[8];
-  void* flags[8];
   void* epoch;
   int rank, world;
-  int cap_floats, cap_flags;
+  int cap_words;
 } b200awq_peers;
 
 int b200awq_w4a16_gemv_allreduce(const void* x, const void* qweight, const void* scales, const void* szeros,

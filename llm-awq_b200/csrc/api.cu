@@ -78,6 +78,7 @@ b200awq::UmmaTuning umma_tuning() {
   t.tn = env_int("B200AWQ_UMMA_TN", 0);
   t.max_ctas = env_int("B200AWQ_UMMA_CTAS", 0);
   t.split = env_int("B200AWQ_UMMA_SPLIT", 0);
+  t.mcast = env_int("B200AWQ_UMMA_MC", -1);
   return t;
 }
 
@@ -105,20 +106,17 @@ int b200awq_w4a16_gemv_allreduce(const void* x, const void* qweight, const void*
   if (int e = check_common(x, qweight, scales, szeros, y, m, n, k, group_size, dtype)) return e;
   if (m > 8) return B200AWQ_ERR_BATCH;
   if (!peers || peers->world < 1 || peers->world > 8 || peers->rank < 0 || peers->rank >= peers->world || !peers->epoch ||
-      (long long)peers->cap_floats < (long long)m * n || peers->cap_flags < n / 8)
+      (long long)peers->cap_words < (long long)m * n)
     return B200AWQ_ERR_PEERS;
   b200awq::PeerArgs pa{};
   for (int r = 0; r < peers->world; ++r) {
-    if (!peers->data[r] || !peers->flags[r]) return B200AWQ_ERR_PEERS;
-    pa.data[r] = static_cast<float*>(peers->data[r]);
-    pa.flags[r] = static_cast<unsigned int*>(peers->flags[r]);
+    if (!peers->data[r]) return B200AWQ_ERR_PEERS;
+    pa.data[r] = static_cast<unsigned long long*>(peers->data[r]);
   }
   pa.epoch = static_cast<unsigned int*>(peers->epoch);
   pa.rank = peers->rank;
   pa.world = peers->world;
-  pa.cap = peers->cap_floats;
-  pa.cap_flags = peers->cap_flags;
-  pa.dbg = env_int("B200AWQ_FUSED_DBG", 0);
+  pa.cap = peers->cap_words;
   int r = b200awq::launch_stream(x, qweight, scales, szeros, y, m, n, k, dtype, pdl_enabled(), stream_tuning(),
                                  static_cast<cudaStream_t>(stream), &pa);
   if (r == 0) g_launches.fetch_add(1, std::memory_order_relaxed);

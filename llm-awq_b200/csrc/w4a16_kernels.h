@@ -20,18 +20,16 @@ struct UmmaTuning {
   int tn = 0;      // 0 = auto, else token tile (32 / 64 / 128 / 256)   [env B200AWQ_UMMA_TN]
   int max_ctas = 0;  // 0 = one per SM                                   [env B200AWQ_UMMA_CTAS]
   int split = 0;     // 0 = auto, 1 = never, 2/4/8 = split k over a cluster [env B200AWQ_UMMA_SPLIT]
+  int mcast = -1;    // -1 = auto, 0 = never, 1 = always (activation multicast over CTA pairs) [env B200AWQ_UMMA_MC]
 };
 
 // Row-parallel tensor parallelism: the GEMV epilogue exchanges fp32 partial sums with the peer GPUs through
 // symmetric (peer-mapped) buffers over NVLink and reduces them in the same kernel (w4a16_stream.cu).
 struct PeerArgs {
-  float* data[8];           // data[r]: rank r's exchange buffer as mapped in this process
-  unsigned int* flags[8];   // flags[r]: rank r's flag words
-  unsigned int* epoch;      // this rank's per-row-block epoch counters (device memory, zero-initialised once)
-  int rank, world;          // world == 0: no exchange
-  int cap;                  // floats per (parity, source) region  (>= m * n)
-  int cap_flags;            // flag words per (parity, source) region (>= n / 8)
-  int dbg;                  // tuning probes (env B200AWQ_FUSED_DBG): 1 no flag wait, 2 local writes only, 4 no system fence
+  unsigned long long* data[8];  // data[r]: rank r's exchange buffer ({fp32, epoch} words) as mapped in this process
+  unsigned int* epoch;          // this rank's per-row-block epoch counters (device memory, zero-initialised once)
+  int rank, world;              // world <= 1: no exchange
+  int cap;                      // words per (parity, source) region  (>= m * n)
 };
 
 struct FlatTuning {

@@ -380,51 +380,45 @@ w4a16_stream_kernel(const T* __restrict__ x, const uint16_t* __restrict__ qw, co
   }
   if (pa.world > 1 && rank == 0) {  // the CTA that holds the final sums of this row block (cluster leader if k is split)
     // ---- row-parallel all-reduce fused into the epilogue (one-shot over NVLink peer memory):
-    // every rank writes its fp32 partials of this row block into EVERY rank's exchange buffer, raises a
-    // flag per destination, waits for the flags of all sources and sums the partials in rank order (so all
-    // ranks produce bit-identical outputs).  Epochs are per row block and live in device memory, which
-    // keeps the protocol valid under CUDA-graph replay; regions alternate with the epoch parity.
+    // every rank writes its fp32 partials of this row block into EVERY rank's exchange buffer, then polls the
+    // words of all sources and sums them in rank order.  Epochs are per row block and live in device memory,
+    // which keeps the protocol valid under CUDA-graph replay; regions alternate with the epoch parity, and a
+    // rank can never run two epochs ahead of a peer because it needs that peer's words to finish an epoch.
     __shared__ unsigned int s_ep;
     const int idx = n0 >> 3;
     if (tid == 0) s_ep = pa.epoch[idx] + 1u;
     __syncthreads();
     const unsigned int ep = s_ep;
     const int W = pa.world;
-    const size_t region = (size_t)((ep & 1u) * W + pa.rank) * pa.cap;
+    // Every exchanged element is ONE 8-byte word {fp32 partial, epoch}: the epoch travels with the value, so a
+    // reader that sees the epoch has the value (single-copy atomic 8-byte store) and no system-scope fence or
+    // separate flag is needed (a st.release.sys / ld.acquire.sys pair was measured at ~8 us per kernel).
     for (int e = tid; e < TT * 128; e += kStreamThreads) {
       const int t = e >> 7, row = (e >> 3) & 15, tok = 8 * t + (e & 7);
       if (tok < M && row < R) {
-        const float v = cpart[e];
-        const size_t off = region + (size_t)tok * N + n0 + row;
+        const unsigned int vbits = __float_as_uint(cpart[e]);
+        const size_t off = (size_t)((ep & 1u) * W + pa.rank) * pa.cap + (size_t)tok * N + n0 + row;
         for (int r = 0; r < W; ++r)
-          if (!(pa.dbg & 2) || r == pa.rank) pa.data[r][off] = v;
+          asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(pa.data[r] + off), "r"(vbits), "r"(ep) : "memory");
       }
     }
-    if (!(pa.dbg & 4)) __threadfence_system();
-    __syncthreads();
-    if (tid < W) {
-      unsigned int* dst = pa.flags[tid] + (size_t)((ep & 1u) * W + pa.rank) * pa.cap_flags + idx;
-      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(ep) : "memory");
-      const unsigned int* src = pa.flags[pa.rank] + (size_t)((ep & 1u) * W + tid) * pa.cap_flags + idx;
-      unsigned int seen;
-      do {
-        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(src) : "memory");
-      } while ((int)(seen - ep) < 0 && !(pa.dbg & 1));
-    }
-    __syncthreads();
     for (int e = tid; e < TT * 128; e += kStreamThreads) {
       const int t = e >> 7, row = (e >> 3) & 15, tok = 8 * t + (e & 7);
       if (tok < M && row < R) {
         float v = 0.f;
-        for (int r = 0; r < W; ++r) {
-          const float* srcp = pa.data[pa.rank] + (size_t)((ep & 1u) * W + r) * pa.cap + (size_t)tok * N + n0 + row;
-          float pv;
-          asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(pv) : "l"(srcp) : "memory");
-          v += pv;
+        for (int r = 0; r < W; ++r) {  // fixed rank order: bit-identical results on every rank
+          const unsigned long long* srcp =
+              pa.data[pa.rank] + (size_t)((ep & 1u) * W + r) * pa.cap + (size_t)tok * N + n0 + row;
+          unsigned int vb, fl;
+          do {
+            asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(vb), "=r"(fl) : "l"(srcp) : "memory");
+          } while (fl != ep);
+          v += __uint_as_float(vb);
         }
         y[(size_t)tok * N + n0 + row] = from_float<T>(v);
       }
     }
+    __syncthreads();
     if (tid == 0) pa.epoch[idx] = ep;
   }
   if (rbi + 1 < rbs) __syncthreads();  // `red` / `cpart` are reused by the next row block

@@ -121,28 +121,24 @@ class PeerExchange:
         if self.world > 8:
             raise ValueError("the fused exchange supports at most 8 ranks")
         dev = torch.device("cuda", torch.cuda.current_device())
-        self.cap_floats = max_tokens * max_out_features
-        self.cap_flags = max_out_features // 8
-        self.data = symm_mem.empty(2 * self.world * self.cap_floats, dtype=torch.float32, device=dev)
-        self.flags = symm_mem.empty(2 * self.world * self.cap_flags, dtype=torch.int32, device=dev)
-        self.flags.zero_()
-        self.epoch = torch.zeros(self.cap_flags, dtype=torch.int32, device=dev)
+        self.cap_words = max_tokens * max_out_features
+        # 8-byte words {fp32 partial, epoch}; int64 zeros == epoch 0 everywhere
+        self.data = symm_mem.empty(2 * self.world * self.cap_words, dtype=torch.int64, device=dev)
+        self.data.zero_()
+        self.epoch = torch.zeros(max_out_features // 8, dtype=torch.int32, device=dev)
         hd = symm_mem.rendezvous(self.data, group.group_name)
-        hf = symm_mem.rendezvous(self.flags, group.group_name)
         torch.cuda.synchronize()
-        dist.barrier(group)          # every rank's flags are zero before anybody's first call
+        dist.barrier(group)          # every rank's buffer is zero before anybody's first call
 
         class _Peers(ctypes.Structure):
-            _fields_ = [("data", ctypes.c_void_p * 8), ("flags", ctypes.c_void_p * 8), ("epoch", ctypes.c_void_p),
-                        ("rank", ctypes.c_int), ("world", ctypes.c_int), ("cap_floats", ctypes.c_int),
-                        ("cap_flags", ctypes.c_int)]
+            _fields_ = [("data", ctypes.c_void_p * 8), ("epoch", ctypes.c_void_p), ("rank", ctypes.c_int),
+                        ("world", ctypes.c_int), ("cap_words", ctypes.c_int)]
         p = _Peers()
         for r in range(self.world):
             p.data[r] = int(hd.buffer_ptrs[r])
-            p.flags[r] = int(hf.buffer_ptrs[r])
         p.epoch = self.epoch.data_ptr()
-        p.rank, p.world, p.cap_floats, p.cap_flags = self.rank, self.world, self.cap_floats, self.cap_flags
-        self._struct, self._handles = p, (hd, hf)
+        p.rank, p.world, p.cap_words = self.rank, self.world, self.cap_words
+        self._struct, self._handles = p, (hd,)
         self.ptr = ctypes.cast(ctypes.pointer(p), ctypes.c_void_p)
 
 
@@ -159,7 +155,7 @@ class FusedRowParallelWQLinear(RowParallelWQLinear):
         from .engine import lib
         m = x_local.numel() // x_local.shape[-1]
         loc = self.local
-        if self.world == 1 or m > 8 or m * loc.out_features > self.exchange.cap_floats:
+        if self.world == 1 or m > 8 or m * loc.out_features > self.exchange.cap_words:
             return super().forward(x_local)
         x = x_local if x_local.is_contiguous() else x_local.contiguous()
         y = torch.empty(*x.shape[:-1], loc.out_features, dtype=x.dtype, device=x.device)

@@ -57,7 +57,7 @@ struct FlatParams {
   int nw;      // weight ring slots (4 KB each)
   int nx;      // activation ring slots (TN * 128 B each)
   int ng;      // 128-k groups of this CTA's k range
-  int off_x, off_w, off_sum, off_bar, total;  // shared-memory carve-up (off_x is 1024-aligned at run time)
+  int off_x, off_w, off_sum, off_rbuf, off_bar, total;  // shared-memory carve-up (off_x is 1024-aligned at run time)
 };
 
 // ---------------------------------------------------------------- tcgen05 / TMA PTX (same encodings as w4a16_umma.cu)
@@ -157,8 +157,9 @@ w4a16_flat_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   uint64_t* dfull = aempty + kFlatNA;
   uint64_t* dempty = dfull + 1;
   uint64_t* sfull = dempty + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sfull + 1);
-  float* cpart = reinterpret_cast<float*>(ws);  // [MT][128] fp32 partials; aliases the weight ring after the k loop
+  uint64_t* rbar = sfull + 1;  // split k: counts the bytes the cluster pushes into rbuf
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + 1);
+  float* rbuf = reinterpret_cast<float*>(smem + P.off_rbuf);  // [source rank][slice] fp32 partial sums pushed by the cluster
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = (S > 1) ? (int)cluster_ctarank() : 0;
@@ -183,6 +184,7 @@ w4a16_flat_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     mbar_init(dfull, 1);
     mbar_init(dempty, 4);
     mbar_init(sfull, 1);
+    mbar_init(rbar, 1);
     mbar_fence_init();
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -193,6 +195,7 @@ w4a16_flat_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   }
   f_fence_before();
   __syncthreads();
+  if (S > 1) cluster_sync_all();  // barrier inits visible cluster-wide before any push (before the PDL wait: overlapped)
   f_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t d_tmem = tmem_base;                 // columns [0, 64): accumulators of one pass
@@ -446,33 +449,34 @@ w4a16_flat_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       for (int t = 0; t < MT; ++t)
         if (t < M) y[(size_t)t * N + n] = from_float<T>(acc[t]);
     } else {
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // every dequant warp is done reading the weight ring
-#pragma unroll
-      for (int t = 0; t < MT; ++t) cpart[t * kFlatBM + row] = acc[t];
-    }
-  }
-
-  __syncwarp();  // single-lane roles: reconverge before the (warp-aligned) cluster barrier
-  if (S > 1) {
-    cluster_sync_all();
-    if (warp >= 4) {
-      const int e0 = (int)threadIdx.x - 128;          // 0..127
-      const int total = M * kFlatBM;                   // live partial sums of this tile
+      // split k without cluster barriers / fences at the end (each is a GPU-scope MEMBAR): every rank PUSHES the
+      // partial sums of slice j of the tile into rank j's shared memory (st.async, 4 bytes completed on rank j's
+      // mbarrier per store), then reduces its own slice in fixed source order and stores it.
+      const int total = M * kFlatBM;
       const int per = (total + S - 1) / S;
+#pragma unroll
+      for (int t = 0; t < MT; ++t) {
+        if (t < M) {
+          const int e = t * kFlatBM + row;
+          const int j = e / per;
+          const uint32_t dst = map_to_rank(smem_u32(&rbuf[rank * per + (e - j * per)]), (uint32_t)j);
+          const uint32_t dbar = map_to_rank(smem_u32(rbar), (uint32_t)j);
+          asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(dst),
+                       "r"(__float_as_uint(acc[t])), "r"(dbar)
+                       : "memory");
+        }
+      }
       const int lo = rank * per, hi = min(total, lo + per);
+      const int e0 = (int)threadIdx.x - 128;  // 0..127
+      if (e0 == 0) mbar_expect_tx(rbar, (uint32_t)(hi > lo ? (hi - lo) * S * 4 : 0));
+      mbar_wait(rbar, 0);
       for (int e = lo + e0; e < hi; e += 128) {
-        const uint32_t a = smem_u32(&cpart[e]);
-        float pv[8];  // all remote loads in flight at once (cluster size <= 8), then a fixed-order sum
-#pragma unroll
-        for (int r = 0; r < 8; ++r) pv[r] = (r < S) ? ld_cluster_f32(map_to_rank(a, (uint32_t)r)) : 0.f;
         float v = 0.f;
-#pragma unroll
-        for (int r = 0; r < 8; ++r) v += pv[r];
+        for (int r = 0; r < S; ++r) v += rbuf[r * per + (e - lo)];
         const int t = e / kFlatBM, rr = e - t * kFlatBM;
         y[(size_t)t * N + rt * kFlatBM + rr] = from_float<T>(v);
       }
     }
-    cluster_sync_all();  // keep every CTA's shared memory alive until all ranks have read it
   }
 
   FLAT_STAMP(threadIdx.x == 128, 6);
@@ -533,10 +537,11 @@ static int launch_flat_t(const void* x, const void* qw, const void* sc, const vo
   P.nx = P.nst < 8 ? P.nst : 8;
   int off = 0;
   P.off_x = off, off += P.nx * TN * 128;
-  P.off_w = off, off += (P.nw * kFlatWBytes > MT * kFlatBM * 4 ? P.nw * kFlatWBytes : MT * kFlatBM * 4);
+  P.off_w = off, off += P.nw * kFlatWBytes;
   P.off_sum = off, off += (MODE == 2 ? M * P.ng * 8 : 0);
+  P.off_rbuf = off, off += (S > 1 ? (M * kFlatBM + 8 * S) * 4 : 0);
   off = (off + 15) & ~15;
-  P.off_bar = off, off += (2 * P.nw + 2 * P.nx + 2 * kFlatNA + 3) * 8 + 16;
+  P.off_bar = off, off += (2 * P.nw + 2 * P.nx + 2 * kFlatNA + 4) * 8 + 16;
   P.total = off + 1024;  // run-time 1024-byte alignment of the base
   if (P.total > 200 * 1024) return B200AWQ_ERR_SHAPE;
 

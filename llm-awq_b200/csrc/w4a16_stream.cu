@@ -59,7 +59,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 #endif
 
 struct StreamSmem {
-  int w, s, z, x, red, cpart, xsum, bars, total;
+  int w, s, z, x, red, cpart, rbuf, xsum, bars, total;
   int ngroups, nrounds, nbar;  // derived on the host so the kernel prologue has no integer divisions
   int rbs;                     // row blocks (of 8*RO channels) this CTA processes one after the other
 };
@@ -76,8 +76,9 @@ __host__ __device__ inline StreamSmem stream_smem_layout(int RO, int TT, int MOD
   L.x = off, off += M * (Kc * 2 + 16);
   L.red = off, off += kStreamWarps * TT * 128 * 4;
   L.cpart = off, off += TT * 128 * 4;
+  L.rbuf = off, off += 8 * TT * 128 * 4;  // split-k: partial sums pushed by the other CTAs of the cluster
   L.xsum = off, off += (MODE ? 8 * TT * ng * 8 : 0);
-  L.bars = off, off += (rbs * nbar + 1) * 8;
+  L.bars = off, off += (rbs * nbar + 2) * 8;
   L.total = off;
   L.ngroups = ng;
   L.nrounds = (ng + kStreamWarps - 1) / kStreamWarps;
@@ -121,10 +122,12 @@ w4a16_stream_kernel(const T* __restrict__ x, const uint16_t* __restrict__ qw, co
   float2* xsum = reinterpret_cast<float2*>(smem + L.xsum);  // [8 TT tok][group] {X, C}   (MODE 2)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint64_t* xbar = bars + L.rbs * nbar;
+  uint64_t* rbar = xbar + 1;                                 // split-k: counts the bytes pushed into rbuf
+  float* rbuf = reinterpret_cast<float*>(smem + L.rbuf);    // [cluster rank][tt][16][8]
 
   // ---- weight prefetch: 2*RO quad rows x nbar pieces of (rpb * 1024 k = 2 rpb KB), k-major issue order
   if (tid == 0) {
-    for (int b = 0; b <= L.rbs * nbar; ++b) mbar_init(&bars[b], 1);
+    for (int b = 0; b <= L.rbs * nbar + 1; ++b) mbar_init(&bars[b], 1);
     mbar_fence_init();
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     B200AWQ_STAMP(7);
@@ -164,6 +167,7 @@ w4a16_stream_kernel(const T* __restrict__ x, const uint16_t* __restrict__ qw, co
     }
   }
   __syncthreads();  // barrier inits and the zeroed correction terms visible to everyone
+  if (S > 1) cluster_sync_all();  // ... and to the other CTAs of the cluster, BEFORE the wait (overlaps the previous kernel)
   B200AWQ_STAMP(2);
   pdl_wait_prior_grid();  // activations (and y) belong to the stream order from here on
   B200AWQ_STAMP(3);
@@ -359,24 +363,34 @@ w4a16_stream_kernel(const T* __restrict__ x, const uint16_t* __restrict__ qw, co
     }
   }
   if (S > 1) {
-    cluster_sync_all();
-    if (rank == 0) {
+    // split-k reduce WITHOUT cluster barriers or fences at the end of the kernel (each of them is lowered to a
+    // GPU-scope MEMBAR): the other CTAs PUSH their partial sums into the leader's shared memory with st.async,
+    // every store completing 4 bytes on the leader's mbarrier; they can exit right away.
+    const int nvalid = M * R;  // live (token, channel) sums per CTA
+    if (rank != 0) {
+      const uint32_t dst_bar = map_to_rank(smem_u32(rbar), 0);
       for (int e = tid; e < TT * 128; e += kStreamThreads) {
         const int t = e >> 7, row = (e >> 3) & 15, tok = 8 * t + (e & 7);
         if (tok < M && row < R) {
-          const uint32_t a = smem_u32(&cpart[e]);
-          float pv[8];  // all remote loads in flight at once (cluster size <= 8), then a fixed-order sum
-#pragma unroll
-          for (int r = 0; r < 8; ++r) pv[r] = (r < S) ? ld_cluster_f32(map_to_rank(a, (uint32_t)r)) : 0.f;
-          float v = 0.f;
-#pragma unroll
-          for (int r = 0; r < 8; ++r) v += pv[r];
+          const uint32_t dst = map_to_rank(smem_u32(&rbuf[rank * TT * 128 + e]), 0);
+          asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(dst),
+                       "r"(__float_as_uint(cpart[e])), "r"(dst_bar)
+                       : "memory");
+        }
+      }
+    } else {
+      if (tid == 0) mbar_expect_tx(rbar, (uint32_t)((S - 1) * nvalid * 4));
+      mbar_wait(rbar, (uint32_t)(rbi & 1));
+      for (int e = tid; e < TT * 128; e += kStreamThreads) {
+        const int t = e >> 7, row = (e >> 3) & 15, tok = 8 * t + (e & 7);
+        if (tok < M && row < R) {
+          float v = cpart[e];
+          for (int r = 1; r < S; ++r) v += rbuf[r * TT * 128 + e];  // fixed order
           if (pa.world > 1) cpart[e] = v;  // only this thread reads / writes the leader's own cpart[e]
           else y[(size_t)tok * N + n0 + row] = from_float<T>(v);
         }
       }
     }
-    cluster_sync_all();  // keep every CTA's shared memory alive until the leader has read it
   }
   if (pa.world > 1 && rank == 0) {  // the CTA that holds the final sums of this row block (cluster leader if k is split)
     // ---- row-parallel all-reduce fused into the epilogue (one-shot over NVLink peer memory):

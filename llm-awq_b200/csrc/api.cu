@@ -139,7 +139,13 @@ int b200awq_w4a16_gemm(const void* x, const void* qweight, const void* scales, c
   if (r == B200AWQ_ERR_SHAPE && m <= stream_max_m && m <= 16)
     r = b200awq::launch_stream(x, qweight, scales, szeros, y, m, n, k, dtype, pdl_enabled(), stream_tuning(),
                                static_cast<cudaStream_t>(stream));
-  if (r == B200AWQ_ERR_SHAPE)  // too many tokens for the streaming kernel (or its k slice does not fit on chip)
+  if (r == B200AWQ_ERR_SHAPE && env_int("B200AWQ_UMMA2", 0) == 1 && n % 256 == 0) {
+    // opt-in: second-generation prefill kernel (256 channels x 128 tokens per CTA, w4a16_umma2.cu).  It moves a third
+    // less L2 -> SM traffic per MAC but measured ~10% SLOWER than the 128 x 256 kernel (profiles/README.md).
+    r = b200awq::launch_umma2(x, qweight, scales, szeros, y, m, n, k, dtype, pdl_enabled(), umma_tuning(),
+                              static_cast<cudaStream_t>(stream));
+  }
+  if (r == B200AWQ_ERR_SHAPE)  // 128-channel tiles; split-k over a cluster for small token counts
     r = b200awq::launch_umma(x, qweight, scales, szeros, y, m, n, k, dtype, pdl_enabled(), umma_tuning(),
                              static_cast<cudaStream_t>(stream));
   if (r == 0) g_launches.fetch_add(1, std::memory_order_relaxed);

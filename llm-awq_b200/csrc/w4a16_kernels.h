@@ -44,6 +44,10 @@ int launch_stream(const void* x, const void* qw, const void* sc, const void* sz,
 int launch_umma(const void* x, const void* qw, const void* sc, const void* sz, void* y, int M, int N, int K, int dtype,
                 bool pdl, const UmmaTuning& tune, cudaStream_t stream);
 
+// second-generation prefill kernel: 256 channels x 128 tokens per CTA, N % 256 == 0 (w4a16_umma2.cu)
+int launch_umma2(const void* x, const void* qw, const void* sc, const void* sz, void* y, int M, int N, int K, int dtype,
+                 bool pdl, const UmmaTuning& tune, cudaStream_t stream);
+
 // tcgen05 skinny-batch kernel, 1 <= M <= 64, N % 128 == 0 (w4a16_flat.cu)
 int launch_flat(const void* x, const void* qw, const void* sc, const void* sz, void* y, int M, int N, int K, int dtype,
                 bool pdl, const FlatTuning& tune, cudaStream_t stream);

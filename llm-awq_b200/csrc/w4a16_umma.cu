@@ -302,7 +302,15 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       const int n = oc_tile * kBM + row;
       const uint16_t* sp = reinterpret_cast<const uint16_t*>(scales) + (size_t)(kb0 / 2) * N + n;
       const uint16_t* zp = reinterpret_cast<const uint16_t*>(szeros) + (size_t)(kb0 / 2) * N + n;
-      uint16_t s_nxt = __ldg(sp), z_nxt = __ldg(zp);
+      // scale / zero of this thread's channel, fetched FOUR 128-k groups ahead (a group = one stage of this warp
+      // group; one group ahead left the global-load latency exposed at every stage: profiles/README.md)
+      const int ngk = num_kb / 2;
+      uint16_t sq[4], zq[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        sq[i] = (i < ngk) ? __ldg(sp + (size_t)i * N) : (uint16_t)0;
+        zq[i] = (i < ngk) ? __ldg(zp + (size_t)i * N) : (uint16_t)0;
+      }
       uint32_t s2 = 0, z2 = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         if ((kb & 1) != grp) {  // the other group's stage (num_kb is even: a 128-k group is one stage of each)
@@ -310,11 +318,13 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           if (++as == kAStages) as = 0, aph ^= 1;
           continue;
         }
-        s2 = splat16(s_nxt);
-        z2 = splat16(z_nxt);
-        if (kb + 2 < num_kb) {
-          s_nxt = __ldg(sp + (size_t)(kb / 2 + 1) * N);
-          z_nxt = __ldg(zp + (size_t)(kb / 2 + 1) * N);
+        s2 = splat16(sq[0]);
+        z2 = splat16(zq[0]);
+        sq[0] = sq[1], sq[1] = sq[2], sq[2] = sq[3];
+        zq[0] = zq[1], zq[1] = zq[2], zq[2] = zq[3];
+        if (kb / 2 + 4 < ngk) {
+          sq[3] = __ldg(sp + (size_t)(kb / 2 + 4) * N);
+          zq[3] = __ldg(zp + (size_t)(kb / 2 + 4) * N);
         }
         mbar_wait(&full[s], ph);
         const uint8_t* wp = ws + s * kWBytes + (row >> 2) * 128 + (row & 3) * 32;

@@ -78,7 +78,6 @@ b200awq::UmmaTuning umma_tuning() {
   t.tn = env_int("B200AWQ_UMMA_TN", 0);
   t.max_ctas = env_int("B200AWQ_UMMA_CTAS", 0);
   t.split = env_int("B200AWQ_UMMA_SPLIT", 0);
-  t.mcast = env_int("B200AWQ_UMMA_MC", -1);
   return t;
 }
 

@@ -20,7 +20,6 @@ struct UmmaTuning {
   int tn = 0;      // 0 = auto, else token tile (32 / 64 / 128 / 256)   [env B200AWQ_UMMA_TN]
   int max_ctas = 0;  // 0 = one per SM                                   [env B200AWQ_UMMA_CTAS]
   int split = 0;     // 0 = auto, 1 = never, 2/4/8 = split k over a cluster [env B200AWQ_UMMA_SPLIT]
-  int mcast = -1;    // -1 = auto, 0 = never, 1 = always (activation multicast over CTA pairs) [env B200AWQ_UMMA_MC]
 };
 
 // Row-parallel tensor parallelism: the GEMV epilogue exchanges fp32 partial sums with the peer GPUs through

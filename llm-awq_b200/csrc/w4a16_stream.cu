@@ -64,7 +64,8 @@ struct StreamSmem {
   int rbs;                     // row blocks (of 8*RO channels) this CTA processes one after the other
 };
 
-__host__ __device__ inline StreamSmem stream_smem_layout(int RO, int TT, int MODE, int M, int Kc, int rpb, int rbs, int kStreamWarps) {
+__host__ __device__ inline StreamSmem stream_smem_layout(int RO, int TT, int MODE, int M, int Kc, int rpb, int rbs, int kStreamWarps,
+                                                         bool split) {
   StreamSmem L;
   const int ng = Kc / kGroup;
   const int nbar = ((ng + kStreamWarps - 1) / kStreamWarps + rpb - 1) / rpb;
@@ -76,7 +77,7 @@ __host__ __device__ inline StreamSmem stream_smem_layout(int RO, int TT, int MOD
   L.x = off, off += M * (Kc * 2 + 16);
   L.red = off, off += kStreamWarps * TT * 128 * 4;
   L.cpart = off, off += TT * 128 * 4;
-  L.rbuf = off, off += 8 * TT * 128 * 4;  // split-k: partial sums pushed by the other CTAs of the cluster
+  L.rbuf = off, off += (split ? 8 * TT * 128 * 4 : 0);  // split-k: partial sums pushed by the other CTAs of the cluster
   L.xsum = off, off += (MODE ? 8 * TT * ng * 8 : 0);
   L.bars = off, off += (rbs * nbar + 2) * 8;
   L.total = off;
@@ -485,8 +486,8 @@ static int launch_stream_w(const void* x, const void* qw, const void* sc, const 
   const int nblk = N / (8 * RO);
   int rbs = (g_stream_rbs > 0) ? g_stream_rbs : 1;
   if (S != 1 || rbs > nblk) rbs = 1;
-  StreamSmem L = stream_smem_layout(RO, TT, MODE, M, Kc, rpb, rbs, kStreamWarps);
-  if (L.total > kStreamSmemCap && rbs > 1) rbs = 1, L = stream_smem_layout(RO, TT, MODE, M, Kc, rpb, 1, kStreamWarps);
+  StreamSmem L = stream_smem_layout(RO, TT, MODE, M, Kc, rpb, rbs, kStreamWarps, S > 1);
+  if (L.total > kStreamSmemCap && rbs > 1) rbs = 1, L = stream_smem_layout(RO, TT, MODE, M, Kc, rpb, 1, kStreamWarps, S > 1);
   if (L.total > kStreamSmemCap) return B200AWQ_ERR_SHAPE;
   constexpr int kStreamThreads = kStreamWarps * 32;
   auto kern = w4a16_stream_kernel<T, RO, TT, MODE, kStreamWarps>;

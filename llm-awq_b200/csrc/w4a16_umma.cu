@@ -48,14 +48,6 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
-__device__ __forceinline__ void tma_load_2d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
-                                               uint16_t cta_mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
-          smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
-      : "memory");
-}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -63,13 +55,6 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-// the same arrival delivered to the barrier at this offset in every CTA of `cta_mask` (activation multicast mode)
-__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t cta_mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                   smem_u32(bar)),
-               "h"(cta_mask)
                : "memory");
 }
 // D[tmem] (+)= A[tmem] * B[smem desc]
@@ -153,7 +138,6 @@ struct UmmaSmem {
 template <typename T, int TN>
 __global__ void __launch_bounds__(kUmmaThreads, 1)
 w4a16_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
-                  const __grid_constant__ CUtensorMap tm_xh, int mc,
                   const T* __restrict__ scales, const T* __restrict__ szeros, T* __restrict__ y, int M, int N, int K, int S) {
   using L = UmmaSmem<TN>;
   constexpr int STAGES = L::kStages;
@@ -177,25 +161,23 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tok_tiles = (M + TN - 1) / TN;
   const int num_tiles = tok_tiles * (N / kBM);
-  // Two uses of a thread-block cluster (mutually exclusive):
-  //  * S > 1  split-K: rank r of S owns k blocks [kb0, kb0 + num_kb) of the SAME tile (small token counts);
-  //  * mc     activation multicast: the 2 CTAs of a cluster compute the two 128-channel halves of a 256-channel
-  //           super tile for the same tokens; each loads HALF of the activation tile and multicasts it to both,
-  //           which halves the L2 -> SM traffic of the operand every CTA would otherwise stream on its own.
-  const int CS = mc ? 2 : S;
+  // split-K over a thread-block cluster (small token counts): rank r of S owns k blocks [kb0, kb0 + num_kb) of the
+  // SAME tile; the cluster walks the tiles together.  (Activation multicast over CTA pairs was tried and removed:
+  // -44 % L2 traffic but the per-stage pair handshake made it slower, profiles/README.md.)
+  const int CS = S;
   const int crank = (CS > 1) ? (int)cluster_ctarank() : 0;
   const int num_kb = K / kBK / S;
-  const int kb0 = mc ? 0 : crank * num_kb;
-  const int num_units = mc ? tok_tiles * (N / kBM / 2) : num_tiles;
+  const int kb0 = crank * num_kb;
+  const int num_units = num_tiles;
   const int tile0 = (CS > 1) ? (int)(blockIdx.x / CS) : (int)blockIdx.x;
   const int tile_step = (CS > 1) ? (int)(gridDim.x / CS) : (int)gridDim.x;
-#define B200AWQ_UNIT_DECODE(unit, oc_tile, tok_tile)                                             \
-  const int oc_tile = mc ? ((unit) / tok_tiles) * 2 + crank : (unit) / tok_tiles;              \
+#define B200AWQ_UNIT_DECODE(unit, oc_tile, tok_tile) \
+  const int oc_tile = (unit) / tok_tiles;            \
   const int tok_tile = (unit) % tok_tiles
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], mc ? 10 : 5);  // multicast mode: a stage is free when BOTH CTAs of the pair have consumed it
+      mbar_init(&empty[i], 5);
     }
     for (int i = 0; i < kAStages; ++i) {
       mbar_init(&afull[i], 4);
@@ -235,14 +217,9 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       for (int tile = tile0; tile < num_units; tile += tile_step) {
         B200AWQ_UNIT_DECODE(tile, oc_tile, tok_tile);
         for (int kb = 0; kb < num_kb; ++kb) {
-          if (mc) mbar_wait_cluster(&empty[s], ph ^ 1);  // (arrivals come from both CTAs of the pair)
-          else mbar_wait(&empty[s], ph ^ 1);
+          mbar_wait(&empty[s], ph ^ 1);
           mbar_expect_tx(&full[s], L::kStageBytes);
-          if (mc)  // my half of the token tile, delivered to both CTAs (same offsets, each CTA's own full[s])
-            tma_load_2d_mc(xs + s * L::kXBytes + crank * (L::kXBytes / 2), &tm_xh, &full[s], (kb0 + kb) * kBK,
-                           tok_tile * TN + crank * (TN / 2), (uint16_t)0x3);
-          else
-            tma_load_2d(xs + s * L::kXBytes, &tm_x, &full[s], (kb0 + kb) * kBK, tok_tile * TN);
+          tma_load_2d(xs + s * L::kXBytes, &tm_x, &full[s], (kb0 + kb) * kBK, tok_tile * TN);
           tma_load_2d(ws + s * kWBytes, &tm_w, &full[s], (kb0 + kb) * kBK, oc_tile * (kBM / 4));
           if (++s == STAGES) {
             s = 0;
@@ -272,8 +249,7 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             umma_ts(d_tmem, a_tmem + as * 32 + kk * 8, bdesc + (uint64_t)(kk * 2) /* +32 B */, idesc,
                     (kb | kk) != 0 ? 1u : 0u);
           }
-          if (mc) tc_commit_mc(&empty[s], (uint16_t)0x3);
-          else tc_commit(&empty[s]);
+          tc_commit(&empty[s]);
           tc_commit(&aempty[as]);
           if (++s == STAGES) {
             s = 0;
@@ -352,7 +328,6 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         if (lane == 0) {
           mbar_arrive(&afull[as]);
           mbar_arrive(&empty[s]);
-          if (mc) mbar_arrive_remote(&empty[s], (uint32_t)(crank ^ 1));
         }
         if (++s == STAGES) {
           s = 0;
@@ -482,7 +457,7 @@ static int sm_count() {
 
 template <typename T, int TN>
 static int launch_umma_t(const void* x, const void* qw, const void* sc, const void* sz, void* y, int M, int N, int K,
-                         bool pdl, int max_ctas, int split, int mcast, cudaStream_t stream) {
+                         bool pdl, int max_ctas, int split, cudaStream_t stream) {
   using L = UmmaSmem<TN>;
   EncodeTiledFn enc = get_encoder();
   if (!enc) return B200AWQ_ERR_DRIVER;
@@ -507,17 +482,6 @@ static int launch_umma_t(const void* x, const void* qw, const void* sc, const vo
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return B200AWQ_ERR_DRIVER;
   }
-  CUtensorMap tm_xh;
-  {
-    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)M};
-    cuuint64_t strides[1] = {(cuuint64_t)K * 2};
-    cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)(TN / 2)};
-    cuuint32_t es[2] = {1, 1};
-    CUresult r = enc(&tm_xh, TypeTraits<T>::kIsBf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
-                     const_cast<void*>(x), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return B200AWQ_ERR_DRIVER;
-  }
   auto kern = w4a16_umma_kernel<T, TN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -532,15 +496,9 @@ static int launch_umma_t(const void* x, const void* qw, const void* sc, const vo
   // each walks K / S and the partial tiles are reduced through distributed shared memory in the epilogue
   int S = 1;
   if (TN <= 64 && split > 1 && split <= 8 && (split & (split - 1)) == 0 && (K / kGroup) % split == 0) S = split;
-  // activation multicast over CTA pairs (see the kernel) halves the L2 -> SM traffic of the token tile, which is what
-  // bounds this kernel at 2048 tokens (12.7 TB/s of L2 reads, profiles/README.md); measured SLOWER than independent
-  // CTAs because the per-stage handshake between the pair costs more than the saved bandwidth -> opt-in only
-  int mc = 0;
-  if (mcast == 1 && S == 1 && TN >= 64 && (N / kBM) % 2 == 0) mc = 1;
-  const int CS = mc ? 2 : S;
-  const int units = mc ? tiles / 2 : tiles;
+  const int CS = S;
   int clusters = sms / CS;
-  if (units < clusters) clusters = units;
+  if (tiles < clusters) clusters = tiles;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(clusters * CS));
   cfg.blockDim = dim3(kUmmaThreads);
@@ -562,7 +520,7 @@ static int launch_umma_t(const void* x, const void* qw, const void* sc, const vo
   }
   cfg.attrs = attrs;
   cfg.numAttrs = na;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tm_x, tm_w, tm_xh, mc, (const T*)sc, (const T*)sz, (T*)y, M, N, K, S);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tm_x, tm_w, (const T*)sc, (const T*)sz, (T*)y, M, N, K, S);
   return e == cudaSuccess ? 0 : (int)e;
 }
 
@@ -591,7 +549,7 @@ int launch_umma(const void* x, const void* qw, const void* sc, const void* sz, v
     }
   }
 #define B200AWQ_UMMA_CASE(TT, TN_) \
-  return launch_umma_t<TT, TN_>(x, qw, sc, sz, y, M, N, K, pdl, tune.max_ctas, split, tune.mcast, stream)
+  return launch_umma_t<TT, TN_>(x, qw, sc, sz, y, M, N, K, pdl, tune.max_ctas, split, stream)
   if (dtype == B200AWQ_DTYPE_F16) {
     switch (tn) {
       case 32: B200AWQ_UMMA_CASE(__half, 32);

@@ -29,14 +29,15 @@ bool pdl_enabled() {
 bool aligned16(const void* p) { return p && (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 int check_device() {
-  static int ok = 0;  // 0 unknown, 1 ok, -1 wrong device
-  if (ok == 0) {
-    int dev = 0, major = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return B200AWQ_ERR_DEVICE;
+  static signed char ok[32] = {};  // per device: 0 unknown, 1 ok, -1 wrong device
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return B200AWQ_ERR_DEVICE;
+  dev &= 31;
+  if (ok[dev] == 0) {
     cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
-    ok = (major == 10) ? 1 : -1;
+    ok[dev] = (major == 10) ? 1 : -1;
   }
-  return ok == 1 ? 0 : B200AWQ_ERR_DEVICE;
+  return ok[dev] == 1 ? 0 : B200AWQ_ERR_DEVICE;
 }
 
 int check_common(const void* x, const void* qw, const void* sc, const void* sz, void* y, int m, int n, int k,

@@ -567,12 +567,8 @@ static int launch_flat_t(const void* x, const void* qw, const void* sc, const vo
       return B200AWQ_ERR_DRIVER;
   }
   auto kern = w4a16_flat_kernel<T, TN, MT, MODE>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
+  static bool attr_set[32] = {};  // per kernel instantiation and device
+  if (cudaError_t ea = ensure_dyn_smem(kern, 200 * 1024, attr_set)) return (int)ea;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(N / kFlatBM) * S);
   cfg.blockDim = dim3(kFlatThreads);

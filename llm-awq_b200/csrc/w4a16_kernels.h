@@ -7,6 +7,20 @@
 
 namespace b200awq {
 
+// Opt a kernel into a large dynamic shared-memory size once PER DEVICE (several GPUs may be driven from one process;
+// function attributes are per device).  `flags` is a function-local static array of the caller.
+template <typename K>
+inline cudaError_t ensure_dyn_smem(K kern, int bytes, bool (&flags)[32]) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  dev &= 31;
+  if (flags[dev]) return cudaSuccess;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) flags[dev] = true;
+  return e;
+}
+
 struct StreamTuning {
   int mode = -1;  // -1 = auto (fp16: 2, bf16: 0); 0 operand-exact, 2 group-factored    [env B200AWQ_STREAM_MODE]
   int kc = 0;     // 0 = auto, else input channels per CTA (K / kc in {1,2,4,8})       [env B200AWQ_STREAM_KC]

@@ -483,12 +483,8 @@ static int launch_umma_t(const void* x, const void* qw, const void* sc, const vo
     if (r != CUDA_SUCCESS) return B200AWQ_ERR_DRIVER;
   }
   auto kern = w4a16_umma_kernel<T, TN>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotalSplit);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
+  static bool attr_set[32] = {};  // per kernel instantiation and device
+  if (cudaError_t ea = ensure_dyn_smem(kern, L::kTotalSplit, attr_set)) return (int)ea;
   const int tiles = ((M + TN - 1) / TN) * (N / kBM);
   int sms = sm_count();
   if (max_ctas > 0 && max_ctas < sms) sms = max_ctas;

@@ -335,12 +335,8 @@ static int launch_umma2_t(const void* x, const void* qw, const void* sc, const v
       return B200AWQ_ERR_DRIVER;
   }
   auto kern = w4a16_umma2_kernel<T>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, k2SmemTotal);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
+  static bool attr_set[32] = {};  // per kernel instantiation and device
+  if (cudaError_t ea = ensure_dyn_smem(kern, k2SmemTotal, attr_set)) return (int)ea;
   static int sms = 0;
   if (!sms) {
     int dev = 0;

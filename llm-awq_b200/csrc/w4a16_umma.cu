@@ -34,9 +34,34 @@
 
 namespace b200awq {
 
+#ifdef B200AWQ_TRACE
+// Debug build only (scripts/umma_probe.py): bit 0 skip the dequant ALU work, bit 1 skip tcgen05.st, bit 2 skip the MMAs,
+// bit 3 skip the activation TMA, bit 4 skip the weight TMA, bit 5 skip the epilogue.  Results are wrong by design; only the timing matters.
+__device__ int g_umma_dbg;
+extern "C" int b200awq_debug_set_umma(int v) { return (int)cudaMemcpyToSymbol(g_umma_dbg, &v, sizeof(int)); }
+#define UMMA_DBG(bit) (dbg & (bit))
+// per-stage clock64 stamps of CTA 0 (events: 0 producer past empty, 1 TMA issued, 2 dequant past full, 3 dequant arrives
+// afull, 4 MMA past afull, 5 MMA committed, 6 tile's dfull seen by epilogue, 7 epilogue done)
+constexpr int kUmmaTraceStages = 256;
+__device__ long long g_umma_trace[8][kUmmaTraceStages];
+extern "C" int b200awq_debug_read_umma_trace(long long* out) {
+  return (int)cudaMemcpyFromSymbol(out, g_umma_trace, sizeof(long long) * 8 * kUmmaTraceStages);
+}
+#define UMMA_STAMP(ev, idx)                                                             \
+  do {                                                                                  \
+    if (blockIdx.x == 0 && (idx) < kUmmaTraceStages) g_umma_trace[ev][idx] = clock64(); \
+  } while (0)
+#else
+#define UMMA_DBG(bit) false
+#define UMMA_STAMP(ev, idx) \
+  do {                      \
+  } while (0)
+#endif
+
 constexpr int kBM = 128;      // output channels per tile (TMEM lanes)
 constexpr int kBK = 64;       // k per pipeline stage
-constexpr int kAStages = 4;   // dequantised-A ring in TMEM (32 columns each)
+// The dequantised-A ring in TMEM has one 32-column slot PER shared-memory stage (slot index == stage index), so one
+// tcgen05.commit per stage frees both and the per-stage hand-offs are: TMA -> full, dequant -> afull, MMA -> empty.
 constexpr int kUmmaThreads = 384;  // 4 service warps + 2 groups of 4 dequantisation / epilogue warps
 constexpr int kWBytes = kBM * kBK / 2;  // 4096: packed weights per stage
 
@@ -129,10 +154,11 @@ struct UmmaSmem {
   static constexpr int kPartBytes = TN <= 64 ? TN * kBM * 4 : 0;  // fp32 partial tile for split-K (TN <= 64 only)
   static constexpr int kTotal = kStages * kStageBytes + kOutBytes + 1024 /*align*/ + 512 /*barriers*/;
   static constexpr int kTotalSplit = kTotal + kPartBytes;
-  static constexpr int kTmemCols = (TN + 32 * kAStages) <= 64    ? 64
-                                   : (TN + 32 * kAStages) <= 128 ? 128
-                                   : (TN + 32 * kAStages) <= 256 ? 256
-                                                                 : 512;
+  static constexpr int kTmemCols = (TN + 32 * kStages) <= 64    ? 64
+                                   : (TN + 32 * kStages) <= 128 ? 128
+                                   : (TN + 32 * kStages) <= 256 ? 256
+                                                                : 512;
+  static_assert(TN + 32 * kStages <= 512, "accumulator + A ring must fit TMEM");
 };
 
 template <typename T, int TN>
@@ -147,17 +173,19 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   uint8_t* ws = xs + STAGES * L::kXBytes;               // [STAGES][4096]
   uint8_t* outb = ws + STAGES * kWBytes;                // [2][32][kOutRow]
   uint64_t* bars = reinterpret_cast<uint64_t*>(outb + L::kOutBytes);
-  uint64_t* full = bars;                  // [STAGES]  TMA -> dequant + MMA
-  uint64_t* empty = full + STAGES;        // [STAGES]  dequant (4) + MMA commit (1) -> TMA
-  uint64_t* afull = empty + STAGES;       // [kAStages] dequant (4) -> MMA
-  uint64_t* aempty = afull + kAStages;    // [kAStages] MMA commit -> dequant
-  uint64_t* dfull = aempty + kAStages;    // MMA commit -> epilogue
+  uint64_t* full = bars;                  // [STAGES]  TMA -> dequant (and, transitively through afull, the MMA)
+  uint64_t* empty = full + STAGES;        // [STAGES]  MMA commit -> TMA: smem stage AND TMEM A slot s are free
+  uint64_t* afull = empty + STAGES;       // [STAGES]  dequant (4) -> MMA
+  uint64_t* dfull = afull + STAGES;       // MMA commit -> epilogue
   uint64_t* dempty = dfull + 1;           // epilogue (4) -> MMA
   uint64_t* pfull = dempty + 1;           // split-K: every rank's partial tile is written   (4 S remote arrivals)
   uint64_t* pempty = pfull + 1;           // split-K: every rank has finished reading MY tile (4 S remote arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pempty + 1);
   float* pbuf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);  // [TN][128] fp32 (S > 1 only)
 
+#ifdef B200AWQ_TRACE
+  const int dbg = g_umma_dbg;
+#endif
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tok_tiles = (M + TN - 1) / TN;
   const int num_tiles = tok_tiles * (N / kBM);
@@ -177,11 +205,8 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   if (threadIdx.x == 0) {
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 5);
-    }
-    for (int i = 0; i < kAStages; ++i) {
+      mbar_init(&empty[i], 1);
       mbar_init(&afull[i], 4);
-      mbar_init(&aempty[i], 1);
     }
     mbar_init(dfull, 1);
     mbar_init(dempty, 8);
@@ -204,7 +229,7 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t d_tmem = tmem_base;             // columns [0, TN)
-  const uint32_t a_tmem = tmem_base + TN;        // columns [TN, TN + 32 * kAStages)
+  const uint32_t a_tmem = tmem_base + TN;        // columns [TN, TN + 32 * STAGES)
 
   pdl_launch_dependents();
 
@@ -214,13 +239,16 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       pdl_wait_prior_grid();  // activations come from the previous kernel in the stream
       int s = 0;
       uint32_t ph = 0;
+      [[maybe_unused]] int it = 0;
       for (int tile = tile0; tile < num_units; tile += tile_step) {
         B200AWQ_UNIT_DECODE(tile, oc_tile, tok_tile);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
           mbar_wait(&empty[s], ph ^ 1);
-          mbar_expect_tx(&full[s], L::kStageBytes);
-          tma_load_2d(xs + s * L::kXBytes, &tm_x, &full[s], (kb0 + kb) * kBK, tok_tile * TN);
-          tma_load_2d(ws + s * kWBytes, &tm_w, &full[s], (kb0 + kb) * kBK, oc_tile * (kBM / 4));
+          UMMA_STAMP(0, it);
+          mbar_expect_tx(&full[s], (UMMA_DBG(8) ? 0 : L::kXBytes) + (UMMA_DBG(16) ? 0 : kWBytes));
+          if (!UMMA_DBG(8)) tma_load_2d(xs + s * L::kXBytes, &tm_x, &full[s], (kb0 + kb) * kBK, tok_tile * TN);
+          if (!UMMA_DBG(16)) tma_load_2d(ws + s * kWBytes, &tm_w, &full[s], (kb0 + kb) * kBK, oc_tile * (kBM / 4));
+          UMMA_STAMP(1, it);
           if (++s == STAGES) {
             s = 0;
             ph ^= 1;
@@ -234,30 +262,31 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       constexpr uint32_t kFmt = TypeTraits<T>::kIsBf16 ? 1u : 0u;
       // kind::f16 instruction descriptor: D = f32, A/B = f16|bf16, both K-major, N = TN, M = 128
       constexpr uint32_t idesc = (1u << 4) | (kFmt << 7) | (kFmt << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
-      int s = 0, as = 0;
-      uint32_t ph = 0, aph = 0, dph = 0;
+      int s = 0;
+      uint32_t ph = 0, dph = 0;
+      [[maybe_unused]] int it = 0;
       for (int tile = tile0; tile < num_units; tile += tile_step) {
         mbar_wait(dempty, dph ^ 1);  // accumulator drained by the epilogue of the previous tile
         tc_fence_after();
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full[s], ph);     // activation tile landed
-          mbar_wait(&afull[as], aph);  // dequantised weights are in TMEM
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          // dequantised weights are in TMEM slot s; the dequant warps saw full[s] first, so the activation tile of
+          // the same barrier has landed as well
+          mbar_wait(&afull[s], ph);
+          UMMA_STAMP(4, it);
           tc_fence_after();
           const uint64_t bdesc = make_sw128_desc(smem_u32(xs + s * L::kXBytes));
+          if (!UMMA_DBG(4)) {
 #pragma unroll
-          for (int kk = 0; kk < kBK / 16; ++kk) {
-            umma_ts(d_tmem, a_tmem + as * 32 + kk * 8, bdesc + (uint64_t)(kk * 2) /* +32 B */, idesc,
-                    (kb | kk) != 0 ? 1u : 0u);
+            for (int kk = 0; kk < kBK / 16; ++kk) {
+              umma_ts(d_tmem, a_tmem + s * 32 + kk * 8, bdesc + (uint64_t)(kk * 2) /* +32 B */, idesc,
+                      (kb | kk) != 0 ? 1u : 0u);
+            }
           }
           tc_commit(&empty[s]);
-          tc_commit(&aempty[as]);
+          UMMA_STAMP(5, it);
           if (++s == STAGES) {
             s = 0;
             ph ^= 1;
-          }
-          if (++as == kAStages) {
-            as = 0;
-            aph ^= 1;
           }
         }
         tc_commit(dfull);
@@ -271,9 +300,10 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const int grp = (warp - 4) >> 2;               // the two groups take alternate 64-k stages and alternate epilogue chunks
     const int et = ((warp - 4) & 3) * 32 + lane;  // 0..127 inside the group
-    int s = 0, as = 0;
-    uint32_t ph = 0, aph = 0, dph = 0, pph = 0;
-    for (int tile = tile0; tile < num_units; tile += tile_step) {
+    int s = 0;
+    uint32_t ph = 0, dph = 0, pph = 0;
+    [[maybe_unused]] int it0 = 0, tl = 0;
+    for (int tile = tile0; tile < num_units; tile += tile_step, it0 += num_kb, ++tl) {
       B200AWQ_UNIT_DECODE(tile, oc_tile, tok_tile);
       const int n = oc_tile * kBM + row;
       const uint16_t* sp = reinterpret_cast<const uint16_t*>(scales) + (size_t)(kb0 / 2) * N + n;
@@ -291,7 +321,6 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       for (int kb = 0; kb < num_kb; ++kb) {
         if ((kb & 1) != grp) {  // the other group's stage (num_kb is even: a 128-k group is one stage of each)
           if (++s == STAGES) s = 0, ph ^= 1;
-          if (++as == kAStages) as = 0, aph ^= 1;
           continue;
         }
         s2 = splat16(sq[0]);
@@ -303,11 +332,15 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           zq[3] = __ldg(zp + (size_t)(kb / 2 + 4) * N);
         }
         mbar_wait(&full[s], ph);
+        if (threadIdx.x == 128 + grp * 128) UMMA_STAMP(2, it0 + kb);
         const uint8_t* wp = ws + s * kWBytes + (row >> 2) * 128 + (row & 3) * 32;
         const uint4 w0 = *reinterpret_cast<const uint4*>(wp);
         const uint4 w1 = *reinterpret_cast<const uint4*>(wp + 16);
         uint32_t r[32];
-        {
+        if (UMMA_DBG(1)) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) r[i] = w0.x + i;
+        } else {
           const uint32_t words[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
           for (int b = 0; b < 2; ++b)
@@ -319,29 +352,26 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
               for (int j = 0; j < 4; ++j) r[b * 16 + 4 * j + u] = o[j];  // column = (k in block) / 2
             }
         }
-        mbar_wait(&aempty[as], aph ^ 1);
+        // full[s] was armed only after the commit of the MMAs that last read TMEM slot s: the slot is free
         tc_fence_after();
-        B200AWQ_TMEM_ST32(a_tmem + lane_base + as * 32, r);
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        if (!UMMA_DBG(2)) {
+          B200AWQ_TMEM_ST32(a_tmem + lane_base + s * 32, r);
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&afull[as]);
-          mbar_arrive(&empty[s]);
-        }
+        if (lane == 0) mbar_arrive(&afull[s]);
+        if (threadIdx.x == 128 + grp * 128) UMMA_STAMP(3, it0 + kb);
         if (++s == STAGES) {
           s = 0;
           ph ^= 1;
-        }
-        if (++as == kAStages) {
-          as = 0;
-          aph ^= 1;
         }
       }
       // ------------------------------------------------ epilogue for this tile
       mbar_wait(dfull, dph);
       dph ^= 1;
       tc_fence_after();
+      if (threadIdx.x == 128) UMMA_STAMP(6, tl);
       if (S > 1 && grp == 1) {  // the partial-tile exchange is done by group 0 alone
         tc_fence_before();
         __syncwarp();
@@ -389,7 +419,7 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 #pragma unroll 1
       for (int c = grp; c < TN / 32; c += 2) {
         const int tok0 = tok_tile * TN + c * 32;
-        if (tok0 >= M) break;  // uniform across the group
+        if (tok0 >= M || UMMA_DBG(32)) break;  // uniform across the group
         uint32_t v[32];
         B200AWQ_TMEM_LD32(d_tmem + lane_base + c * 32, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -410,6 +440,7 @@ w4a16_umma_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(dempty);
+      if (threadIdx.x == 128) UMMA_STAMP(7, tl);
     }
     if (S > 1 && grp == 0) mbar_wait_cluster(pempty, pph ^ 1);  // nobody is still reading my last partial tile
   }

@@ -65,14 +65,16 @@ b200awq::FlatTuning flat_tuning() {
   return t;
 }
 // which kernel serves small token counts: B200AWQ_SKINNY = "flat" (tcgen05, default) | "stream" (mma.sync)
-bool use_flat(int m, int n) {
+bool use_flat(int m, int n, int k) {
   static int mode = -1;
   if (mode < 0) {
     const char* v = std::getenv("B200AWQ_SKINNY");
     mode = (v && v[0] == 's') ? 0 : 1;
   }
-  // measured crossovers (profiles/): the mma.sync streaming kernel wins for m <= 4, the tcgen05 kernels above
-  return mode == 1 && n % 128 == 0 && m >= env_int("B200AWQ_FLAT_MIN_M", 5) && m <= env_int("B200AWQ_FLAT_MAX_M", 16);
+  // measured crossovers (profiles/): the mma.sync streaming kernel wins for m <= 4 (m <= 2 when k is long enough to
+  // need a cluster split: 3 <= m <= 4 at k = 14336 is 10 % faster on the tcgen05 kernel), the tcgen05 kernels above
+  const int min_m = env_int("B200AWQ_FLAT_MIN_M", k > 8192 ? 3 : 5);
+  return mode == 1 && n % 128 == 0 && m >= min_m && m <= env_int("B200AWQ_FLAT_MAX_M", 16);
 }
 b200awq::UmmaTuning umma_tuning() {
   b200awq::UmmaTuning t;
@@ -91,7 +93,7 @@ int b200awq_w4a16_gemv(const void* x, const void* qweight, const void* scales, c
   if (int e = check_common(x, qweight, scales, szeros, y, m, n, k, group_size, dtype)) return e;
   if (m > 7) return B200AWQ_ERR_BATCH;  // reference envelope: gemv_cuda.cu:291-330
   int r = B200AWQ_ERR_SHAPE;
-  if (use_flat(m, n))
+  if (use_flat(m, n, k))
     r = b200awq::launch_flat(x, qweight, scales, szeros, y, m, n, k, dtype, pdl_enabled(), flat_tuning(),
                              static_cast<cudaStream_t>(stream));
   if (r == B200AWQ_ERR_SHAPE)
@@ -133,7 +135,7 @@ int b200awq_w4a16_gemm(const void* x, const void* qweight, const void* scales, c
   if (n % 128) return B200AWQ_ERR_SHAPE;  // reference: N / CTA_N with CTA_N = 128, gemm_cuda.cu:38,1225
   const int stream_max_m = env_int("B200AWQ_STREAM_MAX_M", 16);
   int r = B200AWQ_ERR_SHAPE;
-  if (use_flat(m, n))
+  if (use_flat(m, n, k))
     r = b200awq::launch_flat(x, qweight, scales, szeros, y, m, n, k, dtype, pdl_enabled(), flat_tuning(),
                              static_cast<cudaStream_t>(stream));
   if (r == B200AWQ_ERR_SHAPE && m <= stream_max_m && m <= 16)

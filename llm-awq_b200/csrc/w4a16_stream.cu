@@ -559,7 +559,9 @@ int launch_stream(const void* x, const void* qw, const void* sc, const void* sz,
                   bool pdl, const StreamTuning& tune, cudaStream_t stream, const PeerArgs* peers) {
   if (M < 1 || M > 16 || N % 8 || K % kGroup) return B200AWQ_ERR_SHAPE;
   const int ro = (N % 16 == 0) ? 2 : 1;
-  const int kc_target = M <= 2 ? 4096 : (M <= 8 ? 2048 : 1024);
+  // k per CTA: splitting k over a cluster doubles the CTAs and adds the cluster reduction; up to 4 tokens the unsplit
+  // 4096 measured 1.1-1.5x faster than 2048 (profiles/README.md, batch sweep), above that shared memory for x decides
+  const int kc_target = M <= 4 ? 4096 : (M <= 8 ? 2048 : 1024);
   const int S = pick_splits(K, kc_target, tune.kc);
   const int rpb = tune.rpb > 0 ? tune.rpb : 64;  // default: one barrier (4 large copies) per CTA
   g_stream_rbs = tune.rbs;

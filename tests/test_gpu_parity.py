@@ -62,6 +62,20 @@ def test_gemv_model_shapes(N, K, dtype):
 
 
 @pytest.mark.parametrize("dtype", DTYPES, ids=["f16", "bf16"])
+@pytest.mark.parametrize("M", [3, 4])
+@pytest.mark.parametrize("N,K", [(6144, 4096), (4096, 14336), (4096, 11008), (8192, 3584)])
+def test_gemv_model_shapes_batch_sweep(N, K, M, dtype):
+    """BASELINE configs[4] (bs = 4): 3-4 tokens take k unsplit up to 4096 per CTA in the streaming kernel and the
+    tcgen05 skinny kernel when k > 8192 (api.cu use_flat); both routes against the oracle on the model shapes."""
+    qw, s, z = gen_layer(N, K, dtype, seed=17, device=DEV)
+    x = gen_x(M, K, dtype, seed=5, device=DEV)
+    rc, y = abi_call(P.lib(), x, qw, s, z, M, N, K, dtype, "gemv")
+    assert rc == 0
+    rows = np.arange(0, N, 11)
+    check(y[:, rows], oracle_forward(x, qw, s, z, dtype, rows=rows), dtype)
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=["f16", "bf16"])
 @pytest.mark.parametrize("kind,M", [("gemv", 1), ("gemv", 5), ("gemm", 1), ("gemm", 12), ("gemm", 40), ("gemm", 300)])
 def test_one_hot_reads_back_dequantised_weight_bit_exact(kind, M, dtype):
     N, K = 256, 512

@@ -10,6 +10,10 @@
 //   C. tcgen05.st.32x32b.x32 + wait::st (one warp, then four warps at once); tcgen05.ld.32x32b.x32 + wait::ld.
 //   D. cp.async.bulk (global -> shared) of 4 / 8 / 16 / 32 KB from one thread: issue cycles per copy, and latency
 //      until complete_tx lands (data resident in L2).
+//   E. tcgen05.mma kind::i8, TS form (u8 A in TMEM x s8 B in shared memory -> s32, K = 32 per instruction): a known-answer
+//      check of the operand layouts (A: TMEM lane = row, 32-bit column c = bytes k = 4c .. 4c+3, little endian; B: the
+//      same K-major 128-byte-swizzled tile as for f16, one byte per element) and the issue cost per instruction.
+//   F. two warps issuing kind::f16 MMAs at the same time: is the ~70-cycle issue cost per thread or per SM?
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -257,6 +261,130 @@ __global__ void __launch_bounds__(256, 1) probe_kernel(long long* out, const uin
   }
 }
 
+__device__ __forceinline__ void mma_i8_ts(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}"
+      :
+      : "r"(d), "r"(a), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__host__ __device__ inline int probe_a(int r, int k) { return (r + 3 * k) & 15; }          // u8 operand (a 4-bit weight)
+__host__ __device__ inline int probe_b(int n, int k) { return ((n * 7 + k * 3) % 11) - 5; }  // s8 operand
+
+// out2[0] = mismatches of D (128 x 16, K = 32) against the integer dot products, out2[1..16] = D[lane 1][0..15] as computed,
+// out2[20] / out2[21] = issue cycles per i8 MMA (N = 16 / N = 128), out2[24] = cycles per f16 MMA (N = 16) when TWO
+// warps issue at once (compare with section A), out2[25] the same for the second warp.
+__global__ void __launch_bounds__(256, 1) probe2_kernel(long long* out2, int reps) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* btile = smem;  // 128 rows x 128 B
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 16384);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bars + 8);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 16384 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(btile)[i] = 0;
+  __syncthreads();
+  // B[n][k], n < 16, k < 32: K-major rows of 128 B, 16-byte chunk index XOR (row & 7)  (SWIZZLE_128B)
+  for (int i = threadIdx.x; i < 16 * 32; i += blockDim.x) {
+    const int n = i >> 5, k = i & 31;
+    btile[n * 128 + (((k >> 4) ^ (n & 7)) << 4) + (k & 15)] = (uint8_t)(int8_t)probe_b(n, k);
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 8; ++i) bar_init(&bars[i], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_before();
+  __syncthreads();
+  tc_after();
+  const uint32_t tmem = *slot;
+  const uint32_t d_tmem = tmem, a_tmem = tmem + 256, d2_tmem = tmem + 128;
+  if (warp >= 4) {  // A[r][k]: lane r, column c = bytes 4c .. 4c+3
+    const int r = (warp & 3) * 32 + lane;
+    uint32_t v[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      uint32_t w = 0;
+      if (c < 8)
+        for (int b = 0; b < 4; ++b) w |= (uint32_t)probe_a(r, 4 * c + b) << (8 * b);
+      v[c] = w;
+    }
+    ST32(a_tmem + ((uint32_t)((warp & 3) * 32) << 16), v);
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  tc_before();
+  __syncthreads();
+  tc_after();
+  uint32_t cph = 0;
+  if (threadIdx.x == 0) {
+    // u8 x s8 -> s32, K-major both, M = 128
+    const uint32_t idesc16 = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint64_t bdesc = sw128_desc(s32(btile));
+    mma_i8_ts(d_tmem, a_tmem, bdesc, idesc16, 0);
+    tc_commit(&bars[0]);
+    bar_wait(&bars[0], cph), cph ^= 1;
+  }
+  tc_before();
+  __syncthreads();
+  tc_after();
+  if (warp >= 4) {  // check D[r][n]
+    const int r = (warp & 3) * 32 + lane;
+    uint32_t v[32];
+    LD32(d_tmem + ((uint32_t)((warp & 3) * 32) << 16), v);
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    int bad = 0;
+#pragma unroll
+    for (int n = 0; n < 16; ++n) {
+      int ref = 0;
+      for (int k = 0; k < 32; ++k) ref += probe_a(r, k) * probe_b(n, k);
+      bad += ((int)v[n] != ref);
+      if (r == 1) out2[1 + n] = (int)v[n];
+    }
+    if (bad) atomicAdd(reinterpret_cast<unsigned long long*>(&out2[0]), (unsigned long long)bad);
+  }
+  tc_before();
+  __syncthreads();
+  tc_after();
+  if (threadIdx.x == 0) {
+    const uint64_t bdesc = sw128_desc(s32(btile));
+    for (int t = 0; t < 2; ++t) {
+      const int N = t ? 128 : 16;
+      const uint32_t idesc = (2u << 4) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const long long t0 = clock64();
+      for (int r = 0; r < reps; ++r) mma_i8_ts(d_tmem, a_tmem, bdesc + (uint64_t)((r & 3) * 2), idesc, 1);
+      const long long t1 = clock64();
+      tc_commit(&bars[0]);
+      bar_wait(&bars[0], cph), cph ^= 1;
+      out2[20 + t] = t1 - t0;
+      out2[22 + t] = clock64() - t0;
+    }
+  }
+  __syncthreads();
+  // F: warps 1 and 2 issue f16 MMAs (N = 16) into different accumulators at the same time
+  if ((warp == 1 || warp == 2) && lane == 0) {
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint64_t bdesc = sw128_desc(s32(btile));
+    const uint32_t d = warp == 1 ? d_tmem : d2_tmem;
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) mma_ts(d, a_tmem + (r & 7) * 8, bdesc + (uint64_t)((r & 3) * 2), idesc, 1);
+    const long long t1 = clock64();
+    tc_commit(&bars[warp]);
+    bar_wait(&bars[warp], 0);
+    out2[24 + (warp - 1)] = t1 - t0;
+  }
+  tc_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
 int main(int argc, char** argv) {
   const int reps = argc > 1 ? std::atoi(argv[1]) : 64;
   long long* out = nullptr;
@@ -287,5 +415,27 @@ int main(int argc, char** argv) {
   std::printf("D. cp.async.bulk global(L2) -> shared from one thread, 32 KB in total\n");
   std::printf("   %8s %18s %22s\n", "bytes", "issue per copy", "32 KB landed (cycles)");
   for (int si = 0; si < 4; ++si) std::printf("   %8d %18lld %22lld\n", 4096 << si, h[20 + si * 2], h[21 + si * 2]);
+
+  CK(cudaMemset(out, 0, kSlots * sizeof(long long)));
+  const int smem2 = 16384 + 1024 + 256;
+  for (int it = 0; it < 2; ++it) {
+    if (it) CK(cudaMemset(out, 0, sizeof(long long)));
+    probe2_kernel<<<1, 256, smem2>>>(out, reps);
+    CK(cudaDeviceSynchronize());
+  }
+  CK(cudaMemcpy(h.data(), out, kSlots * sizeof(long long), cudaMemcpyDeviceToHost));
+  std::printf("E. tcgen05.mma kind::i8 TS (u8 A in TMEM x s8 B in smem -> s32), M=128 N=16 K=32: %lld of 2048 outputs differ\n", h[0]);
+  std::printf("   D[row 1][0..15] computed:");
+  for (int n = 0; n < 16; ++n) std::printf(" %lld", h[1 + n]);
+  std::printf("\n   D[row 1][0..15] expected:");
+  for (int n = 0; n < 16; ++n) {
+    int ref = 0;
+    for (int k = 0; k < 32; ++k) ref += probe_a(1, k) * probe_b(n, k);
+    std::printf(" %d", ref);
+  }
+  std::printf("\n   issue cycles per i8 MMA: N=16 %.1f (to complete %.1f), N=128 %.1f (to complete %.1f)\n", (double)h[20] / reps,
+              (double)h[22] / reps, (double)h[21] / reps, (double)h[23] / reps);
+  std::printf("F. two warps issuing f16 MMAs (N=16) at once: %.1f and %.1f cycles per MMA each\n", (double)h[24] / reps,
+              (double)h[25] / reps);
   return 0;
 }

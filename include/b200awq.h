@@ -101,6 +101,10 @@ int gemm_forward_4bit(const void* x, const void* qweight, const void* scales, co
  * previous setting. */
 int b200awq_set_pdl(int enable);
 
+/* The library reads its B200AWQ_* environment knobs once, at the first launch.  Tuning / benchmarking tools that
+ * change the environment inside one process call this to have them read again (thread-safe). */
+void b200awq_reload_config(void);
+
 /* Number of kernels this library has launched since load (monotonic, per process). */
 unsigned long long b200awq_launch_count(void);
 

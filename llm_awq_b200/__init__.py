@@ -1,8 +1,10 @@
-"""Import alias: the package directory is `llm-awq_b200/` (not a valid Python identifier),
-so `import llm_awq_b200` executes that directory's __init__ under this name."""
-import os as _os
+"""llm_awq_b200: B200-native W4A16 quantized-linear path behind llm-awq's WQLinear.
 
-__path__ = [_os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "llm-awq_b200")]
-with open(_os.path.join(__path__[0], "__init__.py")) as _f:
-    exec(compile(_f.read(), _os.path.join(__path__[0], "__init__.py"), "exec"))
-del _os, _f
+Only what the hot path needs:
+  csrc/      hand-written sm_100a CUDA + the C ABI (include/b200awq.h) + the pybind shim
+  engine.py  locates / loads the built artefacts; makes `import awq_inference_engine` resolve here
+  qmodule.py host-side mirror of awq/quantize/qmodule.py (WQLinear, packer)
+  tp.py      column / row sharding of the packed tensors + the one all-reduce
+"""
+from .engine import engine, install, lib  # noqa: F401
+from .qmodule import WQLinear, calculate_zeros_width, pack_intweight, unpack_intweight  # noqa: F401

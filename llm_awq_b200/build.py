@@ -1,10 +1,10 @@
 """In-tree build of the sm_100a library and the `awq_inference_engine` extension.
 
-    python llm-awq_b200/build.py [--force]
+    python llm_awq_b200/build.py [--force]
 
 Produces (git-ignored, shipped to the GPU box by gpurun):
-    llm-awq_b200/lib/libb200awq.so                         C ABI (include/b200awq.h), nvcc, no torch
-    llm-awq_b200/plugin/awq_inference_engine<EXT>.so       pybind shim over it (g++ + torch headers)
+    llm_awq_b200/lib/libb200awq.so                         C ABI (include/b200awq.h), nvcc, no torch
+    llm_awq_b200/plugin/awq_inference_engine<EXT>.so       pybind shim over it (g++ + torch headers)
 """
 import os
 import subprocess
@@ -33,7 +33,7 @@ def _run(cmd):
 
 
 def build_lib(force=False):
-    srcs = [os.path.join(CSRC, f) for f in ("api.cu", "w4a16_stream.cu", "w4a16_umma.cu", "w4a16_umma2.cu", "w4a16_flat.cu")]
+    srcs = [os.path.join(CSRC, f) for f in ("api.cu", "w4a16_ring.cu", "w4a16_stream.cu", "w4a16_umma.cu", "w4a16_flat.cu")]
     deps = srcs + [os.path.join(CSRC, f) for f in ("w4_common.cuh", "w4a16_kernels.h")] + \
         [os.path.join(INCLUDE, "b200awq.h"), __file__]
     if not force and _newer(LIB, deps):
@@ -47,7 +47,7 @@ def build_lib(force=False):
 def build_trace_lib():
     """Debug variant with per-launch timestamps (scripts/trace_chain.py); not part of the product."""
     out = os.path.join(HERE, "lib", "libb200awq_trace.so")
-    srcs = [os.path.join(CSRC, f) for f in ("api.cu", "w4a16_stream.cu", "w4a16_umma.cu", "w4a16_umma2.cu", "w4a16_flat.cu")]
+    srcs = [os.path.join(CSRC, f) for f in ("api.cu", "w4a16_ring.cu", "w4a16_stream.cu", "w4a16_umma.cu", "w4a16_flat.cu")]
     _run([os.environ.get("NVCC", "nvcc")] + NVCC_FLAGS + ["-DB200AWQ_TRACE", "-rdc=true", "-shared", "-o", out] + srcs)
     return out
 

@@ -9,7 +9,6 @@
 
 namespace {
 
-std::atomic<int> g_pdl{-1};  // -1 = read B200AWQ_PDL on first use
 std::atomic<unsigned long long> g_launches{0};
 
 int env_int(const char* name, int dflt) {
@@ -17,27 +16,86 @@ int env_int(const char* name, int dflt) {
   return v && *v ? std::atoi(v) : dflt;
 }
 
-bool pdl_enabled() {
-  int v = g_pdl.load(std::memory_order_relaxed);
-  if (v < 0) {
-    v = env_int("B200AWQ_PDL", 1) ? 1 : 0;
-    g_pdl.store(v, std::memory_order_relaxed);
+// Every environment knob of the library, read ONCE (first launch, or b200awq_reload_config()): the decode path is a
+// few microseconds per call, a dozen getenv() per launch is not free, and the tunings are plain values handed to the
+// launchers -- no mutable globals on the call path.
+struct Config {
+  bool pdl;
+  bool ring;          // B200AWQ_RING=0: never use the persistent ring kernel
+  int ring_max_m;     // largest token count served by the ring kernel
+  bool flat;          // B200AWQ_SKINNY=stream: never use the tcgen05 skinny kernel
+  int flat_min_m, flat_min_m_longk, flat_max_m;
+  int stream_max_m;
+  b200awq::RingTuning ring_t;
+  b200awq::StreamTuning stream_t;
+  b200awq::FlatTuning flat_t;
+  b200awq::UmmaTuning umma_t;
+};
+
+Config read_config() {
+  Config c;
+  c.pdl = env_int("B200AWQ_PDL", 1) != 0;
+  c.ring = env_int("B200AWQ_RING", 1) != 0;
+  c.ring_max_m = env_int("B200AWQ_RING_MAX_M", 4);
+  const char* sk = std::getenv("B200AWQ_SKINNY");
+  c.flat = !(sk && sk[0] == 's');
+  // measured crossovers (profiles/): the tcgen05 skinny kernel from 5 tokens (from 3 when k is long enough to need a
+  // cluster split), the tcgen05 tile kernel above 16
+  c.flat_min_m = env_int("B200AWQ_FLAT_MIN_M", 5);
+  c.flat_min_m_longk = env_int("B200AWQ_FLAT_MIN_M", 3);
+  c.flat_max_m = env_int("B200AWQ_FLAT_MAX_M", 16);
+  c.stream_max_m = env_int("B200AWQ_STREAM_MAX_M", 16);
+  c.ring_t.mode = env_int("B200AWQ_RING_MODE", -1);
+  c.ring_t.split = env_int("B200AWQ_RING_SPLIT", 0);
+  c.ring_t.slots = env_int("B200AWQ_RING_SLOTS", 0);
+  c.stream_t.mode = env_int("B200AWQ_STREAM_MODE", -1);
+  c.stream_t.kc = env_int("B200AWQ_STREAM_KC", 0);
+  c.stream_t.rpb = env_int("B200AWQ_STREAM_RPB", 0);
+  c.stream_t.pad = env_int("B200AWQ_STREAM_PAD", 0);
+  c.stream_t.rbs = env_int("B200AWQ_STREAM_RBS", 0);
+  c.stream_t.warps = env_int("B200AWQ_STREAM_WARPS", 0);
+  c.flat_t.kc = env_int("B200AWQ_FLAT_KC", 0);
+  c.umma_t.tn = env_int("B200AWQ_UMMA_TN", 0);
+  c.umma_t.max_ctas = env_int("B200AWQ_UMMA_CTAS", 0);
+  c.umma_t.split = env_int("B200AWQ_UMMA_SPLIT", 0);
+  return c;
+}
+
+// Double-buffered so that a reload never races a reader: readers take a pointer with acquire, writers publish a
+// fully built copy.
+Config g_cfg_store[2];
+std::atomic<const Config*> g_cfg{nullptr};
+std::atomic<int> g_pdl_override{-1};  // b200awq_set_pdl(): -1 = follow the environment
+
+const Config& cfg() {
+  const Config* c = g_cfg.load(std::memory_order_acquire);
+  if (!c) {
+    static const Config first = read_config();  // thread-safe one-time initialisation
+    g_cfg.store(&first, std::memory_order_release);
+    c = &first;
   }
-  return v != 0;
+  return *c;
+}
+
+bool pdl_enabled() {
+  const int o = g_pdl_override.load(std::memory_order_relaxed);
+  return o < 0 ? cfg().pdl : o != 0;
 }
 
 bool aligned16(const void* p) { return p && (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 int check_device() {
-  static signed char ok[32] = {};  // per device: 0 unknown, 1 ok, -1 wrong device
+  static std::atomic<signed char> ok[32];  // per device: 0 unknown, 1 ok, -1 wrong device
   int dev = 0, major = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return B200AWQ_ERR_DEVICE;
   dev &= 31;
-  if (ok[dev] == 0) {
+  signed char v = ok[dev].load(std::memory_order_relaxed);
+  if (v == 0) {
     cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
-    ok[dev] = (major == 10) ? 1 : -1;
+    v = (major == 10) ? 1 : -1;
+    ok[dev].store(v, std::memory_order_relaxed);
   }
-  return ok[dev] == 1 ? 0 : B200AWQ_ERR_DEVICE;
+  return v == 1 ? 0 : B200AWQ_ERR_DEVICE;
 }
 
 int check_common(const void* x, const void* qw, const void* sc, const void* sz, void* y, int m, int n, int k,
@@ -49,39 +107,30 @@ int check_common(const void* x, const void* qw, const void* sc, const void* sz, 
   return check_device();
 }
 
-b200awq::StreamTuning stream_tuning() {
-  b200awq::StreamTuning t;
-  t.mode = env_int("B200AWQ_STREAM_MODE", -1);
-  t.kc = env_int("B200AWQ_STREAM_KC", 0);
-  t.rpb = env_int("B200AWQ_STREAM_RPB", 0);
-  t.pad = env_int("B200AWQ_STREAM_PAD", 0);
-  t.rbs = env_int("B200AWQ_STREAM_RBS", 0);
-  t.warps = env_int("B200AWQ_STREAM_WARPS", 0);
-  return t;
+// which kernel serves small token counts beyond the ring kernel's range
+bool use_flat(const Config& c, int m, int n, int k) {
+  const int min_m = k > 8192 ? c.flat_min_m_longk : c.flat_min_m;
+  return c.flat && n % 128 == 0 && m >= min_m && m <= c.flat_max_m;
 }
-b200awq::FlatTuning flat_tuning() {
-  b200awq::FlatTuning t;
-  t.kc = env_int("B200AWQ_FLAT_KC", 0);
-  return t;
-}
-// which kernel serves small token counts: B200AWQ_SKINNY = "flat" (tcgen05, default) | "stream" (mma.sync)
-bool use_flat(int m, int n, int k) {
-  static int mode = -1;
-  if (mode < 0) {
-    const char* v = std::getenv("B200AWQ_SKINNY");
-    mode = (v && v[0] == 's') ? 0 : 1;
+
+// Small token counts (decode and the bottom of the batch sweep): ring -> flat -> stream, each returning
+// B200AWQ_ERR_SHAPE (or, for the cluster kernels, a launch-configuration error) when it cannot take the shape.
+int launch_small(const Config& c, const void* x, const void* qw, const void* sc, const void* sz, void* y, int m, int n,
+                 int k, int dtype, cudaStream_t st) {
+  int r = B200AWQ_ERR_SHAPE;
+  if (c.ring && m <= c.ring_max_m) r = b200awq::launch_ring(x, qw, sc, sz, y, m, n, k, dtype, pdl_enabled(), c.ring_t, st);
+  if (r != 0 && use_flat(c, m, n, k)) {
+    r = b200awq::launch_flat(x, qw, sc, sz, y, m, n, k, dtype, pdl_enabled(), c.flat_t, st);
+    if (r > 0) {  // e.g. an unschedulable cluster shape: not the caller's problem, the streaming kernel can take it
+      (void)cudaGetLastError();
+      r = B200AWQ_ERR_SHAPE;
+    }
   }
-  // measured crossovers (profiles/): the mma.sync streaming kernel wins for m <= 4 (m <= 2 when k is long enough to
-  // need a cluster split: 3 <= m <= 4 at k = 14336 is 10 % faster on the tcgen05 kernel), the tcgen05 kernels above
-  const int min_m = env_int("B200AWQ_FLAT_MIN_M", k > 8192 ? 3 : 5);
-  return mode == 1 && n % 128 == 0 && m >= min_m && m <= env_int("B200AWQ_FLAT_MAX_M", 16);
-}
-b200awq::UmmaTuning umma_tuning() {
-  b200awq::UmmaTuning t;
-  t.tn = env_int("B200AWQ_UMMA_TN", 0);
-  t.max_ctas = env_int("B200AWQ_UMMA_CTAS", 0);
-  t.split = env_int("B200AWQ_UMMA_SPLIT", 0);
-  return t;
+  if (r != 0 && m <= 16 && m <= c.stream_max_m) {
+    if (r > 0) (void)cudaGetLastError();
+    r = b200awq::launch_stream(x, qw, sc, sz, y, m, n, k, dtype, pdl_enabled(), c.stream_t, st);
+  }
+  return r;
 }
 
 }  // namespace
@@ -92,13 +141,7 @@ int b200awq_w4a16_gemv(const void* x, const void* qweight, const void* scales, c
                        int k, int group_size, int dtype, void* stream) {
   if (int e = check_common(x, qweight, scales, szeros, y, m, n, k, group_size, dtype)) return e;
   if (m > 7) return B200AWQ_ERR_BATCH;  // reference envelope: gemv_cuda.cu:291-330
-  int r = B200AWQ_ERR_SHAPE;
-  if (use_flat(m, n, k))
-    r = b200awq::launch_flat(x, qweight, scales, szeros, y, m, n, k, dtype, pdl_enabled(), flat_tuning(),
-                             static_cast<cudaStream_t>(stream));
-  if (r == B200AWQ_ERR_SHAPE)
-    r = b200awq::launch_stream(x, qweight, scales, szeros, y, m, n, k, dtype, pdl_enabled(), stream_tuning(),
-                               static_cast<cudaStream_t>(stream));
+  const int r = launch_small(cfg(), x, qweight, scales, szeros, y, m, n, k, dtype, static_cast<cudaStream_t>(stream));
   if (r == 0) g_launches.fetch_add(1, std::memory_order_relaxed);
   return r;
 }
@@ -119,7 +162,7 @@ int b200awq_w4a16_gemv_allreduce(const void* x, const void* qweight, const void*
   pa.rank = peers->rank;
   pa.world = peers->world;
   pa.cap = peers->cap_words;
-  int r = b200awq::launch_stream(x, qweight, scales, szeros, y, m, n, k, dtype, pdl_enabled(), stream_tuning(),
+  int r = b200awq::launch_stream(x, qweight, scales, szeros, y, m, n, k, dtype, pdl_enabled(), cfg().stream_t,
                                  static_cast<cudaStream_t>(stream), &pa);
   if (r == 0) g_launches.fetch_add(1, std::memory_order_relaxed);
   return r;
@@ -133,22 +176,11 @@ int b200awq_w4a16_gemm(const void* x, const void* qweight, const void* scales, c
   (void)workspace_bytes;
   if (int e = check_common(x, qweight, scales, szeros, y, m, n, k, group_size, dtype)) return e;
   if (n % 128) return B200AWQ_ERR_SHAPE;  // reference: N / CTA_N with CTA_N = 128, gemm_cuda.cu:38,1225
-  const int stream_max_m = env_int("B200AWQ_STREAM_MAX_M", 16);
+  const Config& c = cfg();
   int r = B200AWQ_ERR_SHAPE;
-  if (use_flat(m, n, k))
-    r = b200awq::launch_flat(x, qweight, scales, szeros, y, m, n, k, dtype, pdl_enabled(), flat_tuning(),
-                             static_cast<cudaStream_t>(stream));
-  if (r == B200AWQ_ERR_SHAPE && m <= stream_max_m && m <= 16)
-    r = b200awq::launch_stream(x, qweight, scales, szeros, y, m, n, k, dtype, pdl_enabled(), stream_tuning(),
-                               static_cast<cudaStream_t>(stream));
-  if (r == B200AWQ_ERR_SHAPE && env_int("B200AWQ_UMMA2", 0) == 1 && n % 256 == 0) {
-    // opt-in: second-generation prefill kernel (256 channels x 128 tokens per CTA, w4a16_umma2.cu).  It moves a third
-    // less L2 -> SM traffic per MAC but measured ~10% SLOWER than the 128 x 256 kernel (profiles/README.md).
-    r = b200awq::launch_umma2(x, qweight, scales, szeros, y, m, n, k, dtype, pdl_enabled(), umma_tuning(),
-                              static_cast<cudaStream_t>(stream));
-  }
-  if (r == B200AWQ_ERR_SHAPE)  // 128-channel tiles; split-k over a cluster for small token counts
-    r = b200awq::launch_umma(x, qweight, scales, szeros, y, m, n, k, dtype, pdl_enabled(), umma_tuning(),
+  if (m <= 16) r = launch_small(c, x, qweight, scales, szeros, y, m, n, k, dtype, static_cast<cudaStream_t>(stream));
+  if (r == B200AWQ_ERR_SHAPE)  // 128-channel tcgen05 tiles; split-k over a cluster for small token counts
+    r = b200awq::launch_umma(x, qweight, scales, szeros, y, m, n, k, dtype, pdl_enabled(), c.umma_t,
                              static_cast<cudaStream_t>(stream));
   if (r == 0) g_launches.fetch_add(1, std::memory_order_relaxed);
   return r;
@@ -164,9 +196,16 @@ int gemm_forward_4bit(const void* x, const void* qweight, const void* scales, co
 }
 
 int b200awq_set_pdl(int enable) {
-  int prev = pdl_enabled() ? 1 : 0;
-  g_pdl.store(enable ? 1 : 0, std::memory_order_relaxed);
+  const int prev = pdl_enabled() ? 1 : 0;
+  g_pdl_override.store(enable ? 1 : 0, std::memory_order_relaxed);
   return prev;
+}
+
+void b200awq_reload_config(void) {
+  static std::atomic<int> which{0};
+  const int w = which.fetch_add(1, std::memory_order_relaxed) & 1;
+  g_cfg_store[w] = read_config();
+  g_cfg.store(&g_cfg_store[w], std::memory_order_release);
 }
 
 unsigned long long b200awq_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

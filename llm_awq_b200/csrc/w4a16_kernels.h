@@ -57,9 +57,16 @@ int launch_stream(const void* x, const void* qw, const void* sc, const void* sz,
 int launch_umma(const void* x, const void* qw, const void* sc, const void* sz, void* y, int M, int N, int K, int dtype,
                 bool pdl, const UmmaTuning& tune, cudaStream_t stream);
 
-// second-generation prefill kernel: 256 channels x 128 tokens per CTA, N % 256 == 0 (w4a16_umma2.cu)
-int launch_umma2(const void* x, const void* qw, const void* sc, const void* sz, void* y, int M, int N, int K, int dtype,
-                 bool pdl, const UmmaTuning& tune, cudaStream_t stream);
+struct RingTuning {
+  int mode = -1;   // -1 = auto (fp16: 2, bf16: 0)                                   [env B200AWQ_RING_MODE]
+  int split = 0;   // 0 = auto, 1 = no k split, 2 = k split over a 2-CTA cluster      [env B200AWQ_RING_SPLIT]
+  int slots = 0;   // 0 = as many ring slots as fit next to a second CTA, else a cap  [env B200AWQ_RING_SLOTS]
+};
+
+// persistent warp-specialised decode kernel, 1 <= M <= 8 (w4a16_ring.cu); returns B200AWQ_ERR_SHAPE when the
+// activations do not fit next to a useful ring (the caller falls back to the kernels below)
+int launch_ring(const void* x, const void* qw, const void* sc, const void* sz, void* y, int M, int N, int K, int dtype,
+                bool pdl, const RingTuning& tune, cudaStream_t stream);
 
 // tcgen05 skinny-batch kernel, 1 <= M <= 64, N % 128 == 0 (w4a16_flat.cu)
 int launch_flat(const void* x, const void* qw, const void* sc, const void* sz, void* y, int M, int N, int K, int dtype,

@@ -36,6 +36,7 @@
 //         Exact in the integer q; differs from MODE 0 only by not rounding q*s+z to T.
 //         Default for fp16 (that rounding is 2^-12 relative: ~2e-4 normwise, inside 1e-3).
 #include <algorithm>
+#include <atomic>
 
 #include "w4_common.cuh"
 #include "w4a16_kernels.h"
@@ -452,12 +453,9 @@ extern "C" int b200awq_debug_read_trace(unsigned long long* host, int count) {
 // ------------------------------------------------------------------------------------ host
 constexpr int kStreamSmemCap = 200 * 1024;
 
-int g_stream_rbs = 0;  // row blocks per CTA: 0 = heuristic (tuning knob B200AWQ_STREAM_RBS)
-int g_stream_pad = 0;  // extra dynamic shared memory per CTA: limits co-residency (tuning knob B200AWQ_STREAM_PAD)
-
-static int next_seq() {
-  static int seq = 0;
-  return seq++;
+static int next_seq() {  // launch counter for the trace build's stamps only
+  static std::atomic<int> seq{0};
+  return seq.fetch_add(1, std::memory_order_relaxed);
 }
 
 static int pick_splits(int K, int kc_target, int kc_env) {
@@ -477,7 +475,7 @@ static int pick_splits(int K, int kc_target, int kc_env) {
 
 template <typename T, int RO, int TT, int MODE, int kStreamWarps>
 static int launch_stream_w(const void* x, const void* qw, const void* sc, const void* sz, void* y, int M, int N, int K,
-                           int S, int rpb, bool pdl, cudaStream_t stream, const PeerArgs* peers) {
+                           int S, int rpb, bool pdl, const StreamTuning& tune, cudaStream_t stream, const PeerArgs* peers) {
   const int Kc = K / S;
   PeerArgs pa{};
   if (peers) pa = *peers;
@@ -486,7 +484,7 @@ static int launch_stream_w(const void* x, const void* qw, const void* sc, const 
   // tuning knob only: fat long-lived CTAs keep the NEXT launch's CTAs from becoming resident, which costs more
   // than the saved prologues (measured, profiles/README.md)
   const int nblk = N / (8 * RO);
-  int rbs = (g_stream_rbs > 0) ? g_stream_rbs : 1;
+  int rbs = (tune.rbs > 0) ? tune.rbs : 1;
   if (S != 1 || rbs > nblk) rbs = 1;
   StreamSmem L = stream_smem_layout(RO, TT, MODE, M, Kc, rpb, rbs, kStreamWarps, S > 1);
   if (L.total > kStreamSmemCap && rbs > 1) rbs = 1, L = stream_smem_layout(RO, TT, MODE, M, Kc, rpb, 1, kStreamWarps, S > 1);
@@ -503,9 +501,9 @@ static int launch_stream_w(const void* x, const void* qw, const void* sc, const 
   size_t dyn = L.total;
   const int ctas = ((nblk + rbs - 1) / rbs) * S;
   const int per_sm = ctas <= 2 * 148 ? 2 : (ctas <= 3 * 148 ? 3 : 0);
-  if (g_stream_pad > 0)
-    dyn += (size_t)g_stream_pad;
-  else if (g_stream_pad == 0 && per_sm > 0 && S == 1)
+  if (tune.pad > 0)  // > 0: explicit extra bytes (limits co-residency), 0: heuristic, < 0: none
+    dyn += (size_t)tune.pad;
+  else if (tune.pad == 0 && per_sm > 0 && S == 1)
     dyn = std::max(dyn, (size_t)(233472 / (per_sm + 1) - 512));
   if (dyn > (size_t)kStreamSmemCap) dyn = L.total;
   cfg.dynamicSmemBytes = dyn;
@@ -531,28 +529,25 @@ static int launch_stream_w(const void* x, const void* qw, const void* sc, const 
   return e == cudaSuccess ? 0 : (int)e;
 }
 
-int g_stream_warps = 0;  // 0 = heuristic, 8 or 16 (tuning knob B200AWQ_STREAM_WARPS)
-
 template <typename T, int RO, int TT, int MODE>
 static int launch_stream_t(const void* x, const void* qw, const void* sc, const void* sz, void* y, int M, int N, int K,
-                           int S, int rpb, bool pdl, cudaStream_t stream, const PeerArgs* peers) {
+                           int S, int rpb, bool pdl, const StreamTuning& tune, cudaStream_t stream, const PeerArgs* peers) {
   // 8 warps per CTA by default; 16 (shorter serial chain after griddepcontrol.wait, half the co-residency) is a knob
-  const int ctas = (N / (8 * RO)) * S;
-  (void)ctas;
-  const int w = g_stream_warps ? g_stream_warps : 8;  // measured (profiles/): 16 warps or several row blocks per CTA do not pay
-  if (w == 16) return launch_stream_w<T, RO, TT, MODE, 16>(x, qw, sc, sz, y, M, N, K, S, rpb, pdl, stream, peers);
-  return launch_stream_w<T, RO, TT, MODE, 8>(x, qw, sc, sz, y, M, N, K, S, rpb, pdl, stream, peers);
+  if (tune.warps == 16)  // measured (profiles/): 16 warps or several row blocks per CTA do not pay
+    return launch_stream_w<T, RO, TT, MODE, 16>(x, qw, sc, sz, y, M, N, K, S, rpb, pdl, tune, stream, peers);
+  return launch_stream_w<T, RO, TT, MODE, 8>(x, qw, sc, sz, y, M, N, K, S, rpb, pdl, tune, stream, peers);
 }
 
 template <typename T, int MODE>
 static int launch_stream_m(const void* x, const void* qw, const void* sc, const void* sz, void* y, int M, int N, int K,
-                           int S, int ro, int rpb, bool pdl, cudaStream_t stream, const PeerArgs* peers) {
+                           int S, int ro, int rpb, bool pdl, const StreamTuning& tune, cudaStream_t stream,
+                           const PeerArgs* peers) {
   if (M <= 8) {
-    if (ro == 2) return launch_stream_t<T, 2, 1, MODE>(x, qw, sc, sz, y, M, N, K, S, rpb, pdl, stream, peers);
-    return launch_stream_t<T, 1, 1, MODE>(x, qw, sc, sz, y, M, N, K, S, rpb, pdl, stream, peers);
+    if (ro == 2) return launch_stream_t<T, 2, 1, MODE>(x, qw, sc, sz, y, M, N, K, S, rpb, pdl, tune, stream, peers);
+    return launch_stream_t<T, 1, 1, MODE>(x, qw, sc, sz, y, M, N, K, S, rpb, pdl, tune, stream, peers);
   }
-  if (ro == 2) return launch_stream_t<T, 2, 2, MODE>(x, qw, sc, sz, y, M, N, K, S, rpb, pdl, stream, peers);
-  return launch_stream_t<T, 1, 2, MODE>(x, qw, sc, sz, y, M, N, K, S, rpb, pdl, stream, peers);
+  if (ro == 2) return launch_stream_t<T, 2, 2, MODE>(x, qw, sc, sz, y, M, N, K, S, rpb, pdl, tune, stream, peers);
+  return launch_stream_t<T, 1, 2, MODE>(x, qw, sc, sz, y, M, N, K, S, rpb, pdl, tune, stream, peers);
 }
 
 int launch_stream(const void* x, const void* qw, const void* sc, const void* sz, void* y, int M, int N, int K, int dtype,
@@ -564,17 +559,14 @@ int launch_stream(const void* x, const void* qw, const void* sc, const void* sz,
   const int kc_target = M <= 4 ? 4096 : (M <= 8 ? 2048 : 1024);
   const int S = pick_splits(K, kc_target, tune.kc);
   const int rpb = tune.rpb > 0 ? tune.rpb : 64;  // default: one barrier (4 large copies) per CTA
-  g_stream_rbs = tune.rbs;
-  g_stream_warps = (tune.warps == 8 || tune.warps == 16) ? tune.warps : 0;
-  g_stream_pad = tune.pad;  // > 0: explicit extra bytes, 0: heuristic, < 0: none
   // default arithmetic: fp16 -> group-factored (MODE 2), bf16 -> operand-exact (MODE 0); see the header comment
   const int mode = (tune.mode == 0 || tune.mode == 2) ? tune.mode : (dtype == B200AWQ_DTYPE_F16 ? 2 : 0);
   if (dtype == B200AWQ_DTYPE_F16) {
-    if (mode == 0) return launch_stream_m<__half, 0>(x, qw, sc, sz, y, M, N, K, S, ro, rpb, pdl, stream, peers);
-    return launch_stream_m<__half, 2>(x, qw, sc, sz, y, M, N, K, S, ro, rpb, pdl, stream, peers);
+    if (mode == 0) return launch_stream_m<__half, 0>(x, qw, sc, sz, y, M, N, K, S, ro, rpb, pdl, tune, stream, peers);
+    return launch_stream_m<__half, 2>(x, qw, sc, sz, y, M, N, K, S, ro, rpb, pdl, tune, stream, peers);
   }
-  if (mode == 0) return launch_stream_m<__nv_bfloat16, 0>(x, qw, sc, sz, y, M, N, K, S, ro, rpb, pdl, stream, peers);
-  return launch_stream_m<__nv_bfloat16, 2>(x, qw, sc, sz, y, M, N, K, S, ro, rpb, pdl, stream, peers);
+  if (mode == 0) return launch_stream_m<__nv_bfloat16, 0>(x, qw, sc, sz, y, M, N, K, S, ro, rpb, pdl, tune, stream, peers);
+  return launch_stream_m<__nv_bfloat16, 2>(x, qw, sc, sz, y, M, N, K, S, ro, rpb, pdl, tune, stream, peers);
 }
 
 }  // namespace b200awq

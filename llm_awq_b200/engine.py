@@ -18,7 +18,7 @@ def lib() -> ctypes.CDLL:
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
-            raise ImportError(f"{LIB_PATH} is not built; run `python llm-awq_b200/build.py`")
+            raise ImportError(f"{LIB_PATH} is not built; run `python llm_awq_b200/build.py`")
         L = ctypes.CDLL(LIB_PATH)
         vp, ci, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
         L.b200awq_w4a16_gemv.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp]

@@ -2,7 +2,7 @@
 
 TEST / BENCH INFRASTRUCTURE ONLY (see oracle/w4a16_oracle.py header): used by
 ``bench.py``'s ``cpu_baseline`` leg and ``bench.py --impl reference`` as the timed CPU arm,
-and by ``tests/`` (checked against the numpy oracle).  Nothing under ``llm-awq_b200/``
+and by ``tests/`` (checked against the numpy oracle).  Nothing under ``llm_awq_b200/``
 imports it.  Parity status: pinned by us, through the numpy oracle (itself pinned to the
 reference's Python packer / quantiser outputs in tests/golden/).
 

@@ -1,6 +1,6 @@
 """CPU oracle for the W4A16 (AWQ v2 / "gemv_new") quantized-linear path.
 
-TEST INFRASTRUCTURE ONLY.  Nothing under ``llm-awq_b200/`` may import this file; only
+TEST INFRASTRUCTURE ONLY.  Nothing under ``llm_awq_b200/`` may import this file; only
 ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
 ``--impl reference`` legs use it, and there only as the checker / the timed CPU arm.
 

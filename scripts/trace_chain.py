@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Debug experiment: how do consecutive GEMV launches overlap?  Uses the TRACE build of the library
-(python llm-awq_b200/build.py --trace) which stamps %globaltimer at 7 points of the first and last CTA.
+(python llm_awq_b200/build.py --trace) which stamps %globaltimer at 7 points of the first and last CTA.
 
     python scripts/trace_chain.py [N K M chain]
 Modes: plain launches / PDL launches / CUDA graph (+-PDL).  Prints us per launch and, for launches in the
@@ -17,7 +17,7 @@ sys.path.insert(0, ROOT)
 from scripts.microbench import make_ring  # noqa: E402
 
 N, K, M, CH = (int(v) for v in (sys.argv[1:5] + ["4096", "4096", "1", "48"][len(sys.argv) - 1:]))
-lib = ctypes.CDLL(os.path.join(ROOT, "llm-awq_b200", "lib", "libb200awq_trace.so"))
+lib = ctypes.CDLL(os.path.join(ROOT, "llm_awq_b200", "lib", "libb200awq_trace.so"))
 vp, ci = ctypes.c_void_p, ctypes.c_int
 lib.b200awq_w4a16_gemv.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp]
 lib.b200awq_w4a16_gemm.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp, ctypes.c_size_t, vp]

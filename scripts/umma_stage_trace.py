@@ -7,7 +7,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from scripts.microbench import make_ring
-lib = ctypes.CDLL(os.path.join(ROOT, "llm-awq_b200", "lib", "libb200awq_trace.so"))
+lib = ctypes.CDLL(os.path.join(ROOT, "llm_awq_b200", "lib", "libb200awq_trace.so"))
 vp, ci = ctypes.c_void_p, ctypes.c_int
 lib.b200awq_w4a16_gemm.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp, ctypes.c_size_t, vp]
 lib.b200awq_debug_set_umma.argtypes = [ci]

@@ -108,7 +108,7 @@ def test_extension_surface_and_no_cpu_fallback():
 
 
 def test_oracle_is_not_imported_by_the_product():
-    pkg = os.path.join(ROOT, "llm-awq_b200")
+    pkg = os.path.join(ROOT, "llm_awq_b200")
     for dirpath, _, files in os.walk(pkg):
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):

@@ -74,14 +74,20 @@ size_t b200awq_w4a16_gemm_workspace_bytes(int m, int n, int k);
  * y holds the full sum on every rank, bit-identical across ranks.
  *   data[r]   rank r's exchange buffer as mapped in this process (symmetric / peer-mapped allocation):
  *             8-byte words {fp32 partial, epoch}, >= 2 * world * cap_words of them, ZERO before the first call
- *   epoch     this rank's private counters (device memory, uint32, >= n_max / 8 elements, ZERO before first use)
- *   cap_words >= m * n.  1 <= m <= 8, world <= 8.  All ranks must issue the same sequence of calls on these
- *   buffers.  Safe under CUDA-graph capture / replay (no host-side state). */
+ *   epoch     this rank's private counters (device memory, uint32, n_max / 8 elements, ZERO before first use)
+ *   n_max     widest layer (out_features) the buffers are sized for, a multiple of 8
+ *   cap_words words per (parity, source rank) region = tok_cap * n_max for some tok_cap >= m; a word's slot is
+ *             channel * tok_cap + token and its epoch counter is the channel's row block, so layers of
+ *             DIFFERENT n (<= n_max) may share one set of buffers.
+ *   1 <= m <= 8, world <= 8.  n > n_max or m > cap_words / n_max is rejected with B200AWQ_ERR_PEERS.  All ranks
+ *   must issue the same sequence of calls on these buffers.  Safe under CUDA-graph capture / replay (no
+ *   host-side state). */
 typedef struct b200awq_peers {
   void* data[8];
   void* epoch;
   int rank, world;
   int cap_words;
+  int n_max;
 } b200awq_peers;
 
 int b200awq_w4a16_gemv_allreduce(const void* x, const void* qweight, const void* scales, const void* szeros,

@@ -151,7 +151,7 @@ int b200awq_w4a16_gemv_allreduce(const void* x, const void* qweight, const void*
   if (int e = check_common(x, qweight, scales, szeros, y, m, n, k, group_size, dtype)) return e;
   if (m > 8) return B200AWQ_ERR_BATCH;
   if (!peers || peers->world < 1 || peers->world > 8 || peers->rank < 0 || peers->rank >= peers->world || !peers->epoch ||
-      (long long)peers->cap_words < (long long)m * n)
+      peers->n_max < 8 || peers->n_max % 8 || n > peers->n_max || peers->cap_words / peers->n_max < m)
     return B200AWQ_ERR_PEERS;
   b200awq::PeerArgs pa{};
   for (int r = 0; r < peers->world; ++r) {
@@ -161,7 +161,8 @@ int b200awq_w4a16_gemv_allreduce(const void* x, const void* qweight, const void*
   pa.epoch = static_cast<unsigned int*>(peers->epoch);
   pa.rank = peers->rank;
   pa.world = peers->world;
-  pa.cap = peers->cap_words;
+  pa.tok_cap = peers->cap_words / peers->n_max;
+  pa.cap = pa.tok_cap * peers->n_max;
   int r = b200awq::launch_stream(x, qweight, scales, szeros, y, m, n, k, dtype, pdl_enabled(), cfg().stream_t,
                                  static_cast<cudaStream_t>(stream), &pa);
   if (r == 0) g_launches.fetch_add(1, std::memory_order_relaxed);

@@ -188,19 +188,20 @@ __device__ __forceinline__ float ld_cluster_f32(uint32_t cluster_addr) {
 }
 
 // ---------------------------------------------------------------- warp-level tensor-core MAC
-// D[16 x 8] = A[16 x 16] * B[16 x 8] + C, fp32 accumulate.  Used by the HBM-bound streaming
+// D[16 x 8] = A[16 x 16] * B[16 x 8] + C, fp32 accumulate.  Not `volatile`: a pure function of its register
+// operands, so the compiler may interleave independent groups.  Used by the HBM-bound streaming
 // kernel only: rows of A are output channels (dequantised in registers), columns of B are
 // tokens.
 template <typename T>
 __device__ __forceinline__ void mma_16816(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                           uint32_t b0, uint32_t b1, const float (&c)[4]) {
   if constexpr (!TypeTraits<T>::kIsBf16) {
-    asm volatile(
+    asm(
         "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
         : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "f"(c[0]), "f"(c[1]), "f"(c[2]), "f"(c[3]));
   } else {
-    asm volatile(
+    asm(
         "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
         : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "f"(c[0]), "f"(c[1]), "f"(c[2]), "f"(c[3]));

@@ -42,7 +42,8 @@ struct PeerArgs {
   unsigned long long* data[8];  // data[r]: rank r's exchange buffer ({fp32, epoch} words) as mapped in this process
   unsigned int* epoch;          // this rank's per-row-block epoch counters (device memory, zero-initialised once)
   int rank, world;              // world <= 1: no exchange
-  int cap;                      // words per (parity, source) region  (>= m * n)
+  int cap;                      // words per (parity, source) region  (= tok_cap * n_max)
+  int tok_cap;                  // tokens a region is laid out for: word slot = channel * tok_cap + token
 };
 
 struct FlatTuning {
@@ -58,7 +59,7 @@ int launch_umma(const void* x, const void* qw, const void* sc, const void* sz, v
                 bool pdl, const UmmaTuning& tune, cudaStream_t stream);
 
 struct RingTuning {
-  int mode = -1;   // -1 = auto (fp16: 2, bf16: 0)                                   [env B200AWQ_RING_MODE]
+  int mode = -1;   // -1 = auto (fp16: 8 for one token else 2, bf16: 0); 0, 2 or 8      [env B200AWQ_RING_MODE]
   int split = 0;   // 0 = auto, 1 = no k split, 2 = k split over a 2-CTA cluster      [env B200AWQ_RING_SPLIT]
   int slots = 0;   // 0 = as many ring slots as fit next to a second CTA, else a cap  [env B200AWQ_RING_SLOTS]
 };

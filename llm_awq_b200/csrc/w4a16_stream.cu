@@ -399,45 +399,50 @@ w4a16_stream_kernel(const T* __restrict__ x, const uint16_t* __restrict__ qw, co
   if (pa.world > 1 && rank == 0) {  // the CTA that holds the final sums of this row block (cluster leader if k is split)
     // ---- row-parallel all-reduce fused into the epilogue (one-shot over NVLink peer memory):
     // every rank writes its fp32 partials of this row block into EVERY rank's exchange buffer, then polls the
-    // words of all sources and sums them in rank order.  Epochs are per row block and live in device memory,
+    // words of all sources and sums them in rank order.  Epochs are per channel OCTET and live in device memory,
     // which keeps the protocol valid under CUDA-graph replay; regions alternate with the epoch parity, and a
     // rank can never run two epochs ahead of a peer because it needs that peer's words to finish an epoch.
-    __shared__ unsigned int s_ep;
+    __shared__ unsigned int s_ep[2];
     const int idx = n0 >> 3;
-    if (tid == 0) s_ep = pa.epoch[idx] + 1u;
+    if (tid < R / 8) s_ep[tid] = pa.epoch[idx + tid] + 1u;
     __syncthreads();
-    const unsigned int ep = s_ep;
     const int W = pa.world;
     // Every exchanged element is ONE 8-byte word {fp32 partial, epoch}: the epoch travels with the value, so a
-    // reader that sees the epoch has the value (single-copy atomic 8-byte store) and no system-scope fence or
-    // separate flag is needed (a st.release.sys / ld.acquire.sys pair was measured at ~8 us per kernel).
+    // reader that sees the epoch has the value (ONE scalar 8-byte access: aligned 64-bit accesses are single-copy
+    // atomic, a .v2.u32 pair is not guaranteed to be) and no system-scope fence or separate flag is needed (a
+    // st.release.sys / ld.acquire.sys pair was measured at ~8 us per kernel).
+    // A word's slot is keyed by (channel, token) and its epoch counter by the channel's octet, i.e. by the SAME
+    // key whatever the layer's n (and this kernel's row-block height) is: layers of different widths can share
+    // one exchange.
     for (int e = tid; e < TT * 128; e += kStreamThreads) {
       const int t = e >> 7, row = (e >> 3) & 15, tok = 8 * t + (e & 7);
       if (tok < M && row < R) {
-        const unsigned int vbits = __float_as_uint(cpart[e]);
-        const size_t off = (size_t)((ep & 1u) * W + pa.rank) * pa.cap + (size_t)tok * N + n0 + row;
+        const unsigned int ep = s_ep[row >> 3];
+        const unsigned long long word = ((unsigned long long)ep << 32) | (unsigned long long)__float_as_uint(cpart[e]);
+        const size_t off = (size_t)((ep & 1u) * W + pa.rank) * pa.cap + (size_t)(n0 + row) * pa.tok_cap + tok;
         for (int r = 0; r < W; ++r)
-          asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(pa.data[r] + off), "r"(vbits), "r"(ep) : "memory");
+          asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(pa.data[r] + off), "l"(word) : "memory");
       }
     }
     for (int e = tid; e < TT * 128; e += kStreamThreads) {
       const int t = e >> 7, row = (e >> 3) & 15, tok = 8 * t + (e & 7);
       if (tok < M && row < R) {
+        const unsigned int ep = s_ep[row >> 3];
         float v = 0.f;
         for (int r = 0; r < W; ++r) {  // fixed rank order: bit-identical results on every rank
           const unsigned long long* srcp =
-              pa.data[pa.rank] + (size_t)((ep & 1u) * W + r) * pa.cap + (size_t)tok * N + n0 + row;
-          unsigned int vb, fl;
+              pa.data[pa.rank] + (size_t)((ep & 1u) * W + r) * pa.cap + (size_t)(n0 + row) * pa.tok_cap + tok;
+          unsigned long long word;
           do {
-            asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(vb), "=r"(fl) : "l"(srcp) : "memory");
-          } while (fl != ep);
-          v += __uint_as_float(vb);
+            asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(word) : "l"(srcp) : "memory");
+          } while ((unsigned int)(word >> 32) != ep);
+          v += __uint_as_float((unsigned int)word);
         }
         y[(size_t)tok * N + n0 + row] = from_float<T>(v);
       }
     }
     __syncthreads();
-    if (tid == 0) pa.epoch[idx] = ep;
+    if (tid < R / 8) pa.epoch[idx + tid] = s_ep[tid];
   }
   if (rbi + 1 < rbs) __syncthreads();  // `red` / `cpart` are reused by the next row block
   }  // rbi

@@ -66,9 +66,11 @@ def shard_fused_qkv(qweight, scales, scaled_zeros, bias, q_out, kv_out, rank, wo
 def _from_tensors(qweight, scales, scaled_zeros, bias, group_size):
     N, K = qweight.shape[0] * 4, qweight.shape[1]
     m = WQLinear(4, group_size, K, N, bias is not None, qweight.device, dtype=scales.dtype)
+    # assign THROUGH the registered buffers (nn.Module.__setattr__ keeps them registered for Tensor values)
     m.qweight, m.scales, m.scaled_zeros = qweight, scales, scaled_zeros
     if bias is not None:
         m.bias = bias
+    assert "qweight" in m._buffers and "scales" in m._buffers and "scaled_zeros" in m._buffers
     return m
 
 
@@ -95,7 +97,8 @@ class RowParallelWQLinear(nn.Module):
         super().__init__()
         t = shard_row(full.qweight, full.scales, full.scaled_zeros, rank, world, full.group_size)
         self.local = _from_tensors(*t, None, full.group_size)
-        self.bias = full.bias
+        # a registered buffer, so that .to() / .cuda() / state_dict() carry it like the reference's WQLinear.bias
+        self.register_buffer("bias", None if full.bias is None else full.bias.detach().clone())
         self.group = group
         self.world = world
 
@@ -121,6 +124,9 @@ class PeerExchange:
         if self.world > 8:
             raise ValueError("the fused exchange supports at most 8 ranks")
         dev = torch.device("cuda", torch.cuda.current_device())
+        if max_out_features % 8:
+            raise ValueError("max_out_features must be a multiple of 8")
+        self.max_tokens, self.max_out_features = max_tokens, max_out_features
         self.cap_words = max_tokens * max_out_features
         # 8-byte words {fp32 partial, epoch}; int64 zeros == epoch 0 everywhere
         self.data = symm_mem.empty(2 * self.world * self.cap_words, dtype=torch.int64, device=dev)
@@ -132,12 +138,12 @@ class PeerExchange:
 
         class _Peers(ctypes.Structure):
             _fields_ = [("data", ctypes.c_void_p * 8), ("epoch", ctypes.c_void_p), ("rank", ctypes.c_int),
-                        ("world", ctypes.c_int), ("cap_words", ctypes.c_int)]
+                        ("world", ctypes.c_int), ("cap_words", ctypes.c_int), ("n_max", ctypes.c_int)]
         p = _Peers()
         for r in range(self.world):
             p.data[r] = int(hd.buffer_ptrs[r])
         p.epoch = self.epoch.data_ptr()
-        p.rank, p.world, p.cap_words = self.rank, self.world, self.cap_words
+        p.rank, p.world, p.cap_words, p.n_max = self.rank, self.world, self.cap_words, max_out_features
         self._struct, self._handles = p, (hd,)
         self.ptr = ctypes.cast(ctypes.pointer(p), ctypes.c_void_p)
 
@@ -155,8 +161,9 @@ class FusedRowParallelWQLinear(RowParallelWQLinear):
         from .engine import lib
         m = x_local.numel() // x_local.shape[-1]
         loc = self.local
-        if self.world == 1 or m > 8 or m * loc.out_features > self.exchange.cap_words:
-            return super().forward(x_local)
+        ex = self.exchange
+        if self.world == 1 or m > 8 or m > ex.max_tokens or loc.out_features > ex.max_out_features:
+            return super().forward(x_local)      # outside what the exchange buffers hold: local kernel + NCCL
         x = x_local if x_local.is_contiguous() else x_local.contiguous()
         y = torch.empty(*x.shape[:-1], loc.out_features, dtype=x.dtype, device=x.device)
         p = lambda t: ctypes.c_void_p(t.data_ptr())

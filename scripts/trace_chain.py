@@ -60,7 +60,8 @@ def dump(tag):
     # pick 6 consecutive launches with the largest seq values present (the last chain executed)
     seqs = sorted(range(1024), key=lambda s: int(t[s, 0, 0]))[-CH:]
     seqs = seqs[CH // 2: CH // 2 + 6]
-    print(f"[{tag}] ABSOLUTE stamps (us): start | issued | pre-wait | wait-ret | x-ready | loop-end | end | bar-init")
+    print(f"[{tag}] ABSOLUTE stamps (us): start | issued | pre-wait | wait-ret | x-ready | loop-end | end | bar-init"
+          "   (ring kernel: start | producer issued all | cluster sync done | wait-ret | x staged | consumers done | finisher done)")
     t0 = int(t[seqs[0], 0, 0])
     for s in seqs:
         for c in (0, 1):

@@ -94,6 +94,14 @@ int b200awq_w4a16_gemv_allreduce(const void* x, const void* qweight, const void*
                                  void* y, int m, int n, int k, int group_size, int dtype,
                                  const b200awq_peers* peers, void* stream);
 
+/* RMSNorm of the decoder layers around the quantised linears: y[i, :] = x[i, :] *
+ * rsqrt(mean(x[i, :]^2) + eps) * gamma, statistics in fp32, one rounding to the element type (fp16 results are
+ * clamped to +-(65504 - 1000) like the reference).  Replaces layernorm_forward_cuda(input, gamma, out, eps)
+ *   reference: awq/kernels/csrc/layernorm/layernorm.cu:38-64 (kernel), :111-131 (host), csrc/pybind.cpp:17.
+ * x, y: [m, n] row-major, gamma: [n]; any n >= 1 (16-byte aligned pointers and n % 8 == 0 take the one-pass
+ * kernel).  m == 0 is a no-op. */
+int b200awq_rmsnorm(const void* x, const void* gamma, void* y, int m, int n, float eps, int dtype, void* stream);
+
 /* Names used by BASELINE.json's north_star; identical to the two launchers above. */
 int gemv_forward_4bit(const void* x, const void* qweight, const void* scales, const void* szeros,
                       void* y, int m, int n, int k, int group_size, int dtype, void* stream);

@@ -17,6 +17,8 @@ LIB = os.path.join(HERE, "lib", "libb200awq.so")
 EXT = os.path.join(HERE, "plugin", "awq_inference_engine" + sysconfig.get_config_var("EXT_SUFFIX"))
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
+KERNEL_SRCS = ("api.cu", "w4a16_ring.cu", "w4a16_stream.cu", "w4a16_umma.cu", "w4a16_flat.cu", "rmsnorm.cu")
+
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC"]
 
@@ -33,7 +35,7 @@ def _run(cmd):
 
 
 def build_lib(force=False):
-    srcs = [os.path.join(CSRC, f) for f in ("api.cu", "w4a16_ring.cu", "w4a16_stream.cu", "w4a16_umma.cu", "w4a16_flat.cu")]
+    srcs = [os.path.join(CSRC, f) for f in KERNEL_SRCS]
     deps = srcs + [os.path.join(CSRC, f) for f in ("w4_common.cuh", "w4a16_kernels.h")] + \
         [os.path.join(INCLUDE, "b200awq.h"), __file__]
     if not force and _newer(LIB, deps):
@@ -47,7 +49,7 @@ def build_lib(force=False):
 def build_trace_lib():
     """Debug variant with per-launch timestamps (scripts/trace_chain.py); not part of the product."""
     out = os.path.join(HERE, "lib", "libb200awq_trace.so")
-    srcs = [os.path.join(CSRC, f) for f in ("api.cu", "w4a16_ring.cu", "w4a16_stream.cu", "w4a16_umma.cu", "w4a16_flat.cu")]
+    srcs = [os.path.join(CSRC, f) for f in KERNEL_SRCS]
     _run([os.environ.get("NVCC", "nvcc")] + NVCC_FLAGS + ["-DB200AWQ_TRACE", "-rdc=true", "-shared", "-o", out] + srcs)
     return out
 

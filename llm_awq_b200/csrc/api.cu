@@ -169,6 +169,17 @@ int b200awq_w4a16_gemv_allreduce(const void* x, const void* qweight, const void*
   return r;
 }
 
+int b200awq_rmsnorm(const void* x, const void* gamma, void* y, int m, int n, float eps, int dtype, void* stream) {
+  if (dtype != B200AWQ_DTYPE_F16 && dtype != B200AWQ_DTYPE_BF16) return B200AWQ_ERR_DTYPE;
+  if (m < 0 || n < 1) return B200AWQ_ERR_SHAPE;
+  if (!x || !gamma || !y) return B200AWQ_ERR_ALIGN;
+  if (int e = check_device()) return e;
+  if (m == 0) return 0;
+  const int r = b200awq::launch_rmsnorm(x, gamma, y, eps, m, n, dtype, pdl_enabled(), static_cast<cudaStream_t>(stream));
+  if (r == 0) g_launches.fetch_add(1, std::memory_order_relaxed);
+  return r;
+}
+
 size_t b200awq_w4a16_gemm_workspace_bytes(int, int, int) { return 0; }
 
 int b200awq_w4a16_gemm(const void* x, const void* qweight, const void* scales, const void* szeros, void* y, int m, int n,

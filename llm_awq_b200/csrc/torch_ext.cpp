@@ -87,10 +87,30 @@ torch::Tensor gemm_forward_cuda_new(torch::Tensor _in_feats, torch::Tensor _kern
   return out;
 }
 
+// reference: awq/kernels/csrc/layernorm/layernorm.cu:111-131 (input [b, s, c], gamma [c], out like input; returns
+// nothing).  Same dtype checks; additionally any rank >= 1 is accepted (rows = numel / last dim), the launch goes to
+// the current stream, and contiguity is checked instead of assumed.
+void layernorm_forward_cuda(torch::Tensor _input, torch::Tensor _gamma, torch::Tensor _out, float eps) {
+  TORCH_CHECK(_input.is_cuda() && _gamma.is_cuda() && _out.is_cuda(), "all tensors must be CUDA tensors");
+  const int dt = dtype_code(_input, "layernorm_forward_cuda");
+  TORCH_CHECK(_gamma.scalar_type() == _input.scalar_type());  // layernorm.cu:122
+  TORCH_CHECK(_out.scalar_type() == _input.scalar_type());    // layernorm.cu:123
+  TORCH_CHECK(_input.dim() >= 1 && _input.is_contiguous() && _out.is_contiguous() && _gamma.is_contiguous(),
+              "inputs must be contiguous");
+  const int64_t n = _input.size(-1);
+  TORCH_CHECK(_gamma.numel() == n && _out.numel() == _input.numel(), "gamma / out do not match input");
+  if (_input.numel() == 0) return;
+  const c10::cuda::CUDAGuard guard(_input.device());
+  raise(b200awq_rmsnorm(_input.data_ptr(), _gamma.data_ptr(), _out.data_ptr(), (int)(_input.numel() / n), (int)n, eps, dt,
+                        at::cuda::getCurrentCUDAStream().stream()),
+        false);
+}
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "B200-native drop-in for llm-awq's awq_inference_engine (W4A16 path only)";
   m.def("gemm_forward_cuda_new", &gemm_forward_cuda_new, "New quantized GEMM kernel.");
   m.def("gemv_forward_cuda_new", &gemv_forward_cuda_new, "New quantized GEMV kernel.");
+  m.def("layernorm_forward_cuda", &layernorm_forward_cuda, "FasterTransformer layernorm kernel");
   m.def("set_pdl", [](bool on) { return b200awq_set_pdl(on ? 1 : 0) != 0; }, "programmatic dependent launch on/off");
   m.def("launch_count", []() { return b200awq_launch_count(); }, "kernels launched by libb200awq so far");
   m.def("version", []() { return std::string(b200awq_version()); });

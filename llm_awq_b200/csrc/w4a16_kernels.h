@@ -73,4 +73,7 @@ int launch_ring(const void* x, const void* qw, const void* sc, const void* sz, v
 int launch_flat(const void* x, const void* qw, const void* sc, const void* sz, void* y, int M, int N, int K, int dtype,
                 bool pdl, const FlatTuning& tune, cudaStream_t stream);
 
+// RMSNorm over the last dimension, one CTA per row (rmsnorm.cu)
+int launch_rmsnorm(const void* x, const void* gamma, void* y, float eps, int m, int n, int dtype, bool pdl, cudaStream_t stream);
+
 }  // namespace b200awq

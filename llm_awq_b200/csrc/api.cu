@@ -21,6 +21,9 @@ int env_int(const char* name, int dflt) {
 // launchers -- no mutable globals on the call path.
 struct Config {
   bool pdl;
+  bool decode;        // B200AWQ_DECODE=0: never use the one-token decode kernel (fp16; bf16 with B200AWQ_DECODE=2)
+  bool decode_bf16;
+  b200awq::DecodeTuning decode_t;
   bool ring;          // B200AWQ_RING=0: never use the persistent ring kernel
   int ring_max_m;     // largest token count served by the ring kernel
   bool flat;          // B200AWQ_SKINNY=stream: never use the tcgen05 skinny kernel
@@ -35,6 +38,11 @@ struct Config {
 Config read_config() {
   Config c;
   c.pdl = env_int("B200AWQ_PDL", 1) != 0;
+  c.decode = env_int("B200AWQ_DECODE", 1) != 0;
+  c.decode_bf16 = env_int("B200AWQ_DECODE", 1) == 2;
+  c.decode_t.split = env_int("B200AWQ_DECODE_SPLIT", 0);
+  c.decode_t.slots = env_int("B200AWQ_DECODE_SLOTS", 0);
+  c.decode_t.warps = env_int("B200AWQ_DECODE_WARPS", 0);
   c.ring = env_int("B200AWQ_RING", 1) != 0;
   c.ring_max_m = env_int("B200AWQ_RING_MAX_M", 4);
   const char* sk = std::getenv("B200AWQ_SKINNY");
@@ -113,12 +121,20 @@ bool use_flat(const Config& c, int m, int n, int k) {
   return c.flat && n % 128 == 0 && m >= min_m && m <= c.flat_max_m;
 }
 
-// Small token counts (decode and the bottom of the batch sweep): ring -> flat -> stream, each returning
+// Small token counts (decode and the bottom of the batch sweep): decode (one token) -> ring -> flat -> stream, each returning
 // B200AWQ_ERR_SHAPE (or, for the cluster kernels, a launch-configuration error) when it cannot take the shape.
 int launch_small(const Config& c, const void* x, const void* qw, const void* sc, const void* sz, void* y, int m, int n,
                  int k, int dtype, cudaStream_t st) {
   int r = B200AWQ_ERR_SHAPE;
-  if (c.ring && m <= c.ring_max_m) r = b200awq::launch_ring(x, qw, sc, sz, y, m, n, k, dtype, pdl_enabled(), c.ring_t, st);
+  // one token: fp16 through the int8-digit decode kernel (bf16 stays operand-exact: dropping the bf16 rounding of
+  // q s + z would move results by ~1e-3 against the reference)
+  if (m == 1 && c.decode && (dtype == B200AWQ_DTYPE_F16 || c.decode_bf16))
+    r = b200awq::launch_decode(x, qw, sc, sz, y, n, k, dtype, pdl_enabled(), c.decode_t, st);
+  if (r > 0) {  // a launch-configuration error (e.g. an unschedulable cluster): the kernels below can take the shape
+    (void)cudaGetLastError();
+    r = B200AWQ_ERR_SHAPE;
+  }
+  if (r != 0 && c.ring && m <= c.ring_max_m) r = b200awq::launch_ring(x, qw, sc, sz, y, m, n, k, dtype, pdl_enabled(), c.ring_t, st);
   if (r != 0 && use_flat(c, m, n, k)) {
     r = b200awq::launch_flat(x, qw, sc, sz, y, m, n, k, dtype, pdl_enabled(), c.flat_t, st);
     if (r > 0) {  // e.g. an unschedulable cluster shape: not the caller's problem, the streaming kernel can take it

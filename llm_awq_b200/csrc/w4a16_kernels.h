@@ -69,6 +69,17 @@ struct RingTuning {
 int launch_ring(const void* x, const void* qw, const void* sc, const void* sz, void* y, int M, int N, int K, int dtype,
                 bool pdl, const RingTuning& tune, cudaStream_t stream);
 
+struct DecodeTuning {
+  int split = 0;   // 0 = auto, else CTAs per cluster = k split (1, 2, 4, 8)            [env B200AWQ_DECODE_SPLIT]
+  int slots = 0;   // 0 = as many ring slots as fit next to a second CTA, else a cap    [env B200AWQ_DECODE_SLOTS]
+  int warps = 0;   // consumer warps per CTA: 8, else 16                                  [env B200AWQ_DECODE_WARPS]
+};
+
+// one-token decode kernel: 8 KB bulk copies, int8-digit tensor-core MACs (w4a16_decode.cu); returns
+// B200AWQ_ERR_SHAPE when the activations do not fit next to a useful ring (the caller falls back)
+int launch_decode(const void* x, const void* qw, const void* sc, const void* sz, void* y, int N, int K, int dtype, bool pdl,
+                  const DecodeTuning& tune, cudaStream_t stream);
+
 // tcgen05 skinny-batch kernel, 1 <= M <= 64, N % 128 == 0 (w4a16_flat.cu)
 int launch_flat(const void* x, const void* qw, const void* sc, const void* sz, void* y, int M, int N, int K, int dtype,
                 bool pdl, const FlatTuning& tune, cudaStream_t stream);

@@ -40,7 +40,8 @@ def chain():
 
 
 def run(tag, flags, env):
-    for k in ("B200AWQ_RING_SLOTS", "B200AWQ_RING_SPLIT", "B200AWQ_RING_MODE"):
+    for k in ("B200AWQ_RING_SLOTS", "B200AWQ_RING_SPLIT", "B200AWQ_RING_MODE", "B200AWQ_DECODE", "B200AWQ_DECODE_SPLIT",
+              "B200AWQ_DECODE_SLOTS", "B200AWQ_DECODE_WARPS"):
         os.environ.pop(k, None)
     os.environ.update(env)
     lib.b200awq_reload_config()
@@ -74,19 +75,23 @@ def run(tag, flags, env):
     for q in seqs:
         for c in (0, 1):
             r = t[q, c]
-            print(f"   seq {q:4d} cta {'first' if c == 0 else 'last '}: " + " ".join(f"{(int(r[i]) - t0) / 1e3:7.2f}" for i in range(7)))
+            print(f"   seq {q:4d} cta {'first' if c == 0 else 'last '}: " + " ".join(f"{(int(r[i]) - t0) / 1e3:7.2f}" for i in range(7)) + f"   x loaded {(int(r[7]) - t0) / 1e3:7.2f}")
     st = (ctypes.c_longlong * 80)()
     assert lib.b200awq_debug_ring_stats(st) == 0
     st = list(st)
-    for w in range(20):
+    if st[77] > 0:
+        print(f"   SM clock over the producer's loop: {st[76]} cycles in {st[77]} ns = {st[76] / st[77] * 1e3:.0f} MHz")
+    for w in range(19):
         a, b, c, n = st[4 * w:4 * w + 4]
         role = "producer" if w == 18 else f"warp {w}"
         if n and (w < 2 or w >= 8):
             print(f"   {role:11s}: wait {a:7d}  work {b:7d}  hand-off {c:7d} cycles over {n} slots  (work/slot {b // n})")
 
 
-run("int8 digits (mode 8)", 0, {})
-run("int8 digits, no k split", 0, {"B200AWQ_RING_SPLIT": "1"})
-run("int8 digits, dry (no math)", 1, {})
-run("fp16 MACs (mode 2)", 0, {"B200AWQ_RING_MODE": "2"})
-run("fp16 MACs, dry", 1, {"B200AWQ_RING_MODE": "2"})
+if M == 1:
+    run("decode kernel (16 consumer warps)", 0, {})
+    run("decode kernel, 8 consumer warps", 0, {"B200AWQ_DECODE_WARPS": "8"})
+    run("decode kernel, dry (no math)", 1, {})
+    run("decode kernel, k split 2", 0, {"B200AWQ_DECODE_SPLIT": "2"})
+    run("decode kernel, no k split", 0, {"B200AWQ_DECODE_SPLIT": "1"})
+run("ring, int8 digits (mode 8)", 0, {"B200AWQ_DECODE": "0"})

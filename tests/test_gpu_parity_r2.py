@@ -95,6 +95,69 @@ def test_ring_partition_edges(N, K, M, dtype):
     check(y, oracle_forward(x, qw, s, z, dtype), dtype)
 
 
+@pytest.mark.parametrize("split", [1, 2, 4])
+@pytest.mark.parametrize("slots", [0, 3])
+@pytest.mark.parametrize("N,K", [(8, 512), (24, 1024), (592, 4096), (600, 4096), (2376, 4224), (4096, 4096), (1280, 8192),
+                                 (4096, 14336), (4104, 11008), (8192, 1024)])
+def test_decode_kernel_splits_and_ring_depths(N, K, split, slots):
+    """The one-token decode kernel with the k split forced to 1 / 2 / 4 CTAs per cluster and with the shallowest ring:
+    quad-row counts below / around the CTA count, row blocks of 4 / 8 / 12 channels at the end of a CTA's range, pieces of
+    fewer than 32 groups (k = 11008: 86 groups), k splits that leave odd group counts."""
+    import os
+    dtype = torch.float16
+    if (K // 128) < split:
+        pytest.skip("fewer groups than ranks")
+    os.environ["B200AWQ_DECODE_SPLIT"] = str(split)
+    os.environ["B200AWQ_DECODE_SLOTS"] = str(slots)
+    P.lib().b200awq_reload_config()
+    try:
+        qw, s, z = gen_layer(N, K, dtype, seed=N + K + split, device=DEV)
+        x = gen_x(1, K, dtype, seed=split, device=DEV)
+        y = _call(x, qw, s, z, 1, N, K, dtype)
+        torch.cuda.synchronize()
+        check(y, oracle_forward(x, qw, s, z, dtype), dtype)
+        y2 = _call(x, qw, s, z, 1, N, K, dtype)
+        assert torch.equal(y, y2)
+    finally:
+        os.environ.pop("B200AWQ_DECODE_SPLIT"), os.environ.pop("B200AWQ_DECODE_SLOTS")
+        P.lib().b200awq_reload_config()
+
+
+def test_decode_kernel_activation_ranges():
+    """The digit decomposition of the activations: huge, tiny, mixed-magnitude and all-zero groups, negative zero,
+    fp16 subnormals.  Exact digits => the result matches the float64 oracle to fp32 accumulation error."""
+    N, K, dtype = 256, 1024, torch.float16
+    qw, s, z = gen_layer(N, K, dtype, seed=77, device=DEV)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(1, K, generator=g)
+    x[0, 0:128] *= 3000.0                      # near the top of the fp16 range
+    x[0, 128:256] *= 1e-4                      # small normals / subnormals
+    x[0, 256:384] = 0.0                        # an all-zero group
+    x[0, 384] = -0.0
+    x[0, 385:512] *= 1e-7                      # flushes to fp16 subnormals / zero
+    x[0, 512:640] = torch.where(torch.arange(128) % 2 == 0, torch.tensor(1000.0), torch.tensor(6e-5))  # 2^24 dynamic range
+    x[0, 640] = 65504.0
+    x = x.to(dtype).to(DEV)
+    y = _call(x, qw, s, z, 1, N, K, dtype)
+    torch.cuda.synchronize()
+    want = oracle_forward(x, qw, s, z, dtype)
+    assert np.isfinite(np64(y)).all()
+    assert rel_err(np64(y), want) < 1e-3
+    # group by group: only one group's activations non-zero -> tight relative check per group
+    for grp in range(8):
+        xk = torch.zeros_like(x)
+        xk[:, grp * 128:(grp + 1) * 128] = x[:, grp * 128:(grp + 1) * 128]
+        yk = _call(xk.contiguous(), qw, s, z, 1, N, K, dtype)
+        wk = oracle_forward(xk, qw, s, z, dtype)
+        if np.linalg.norm(wk) == 0:
+            assert torch.count_nonzero(yk) == 0
+        else:
+            # normwise per group (the kernel uses q s + z unrounded: elementwise it differs from the oracle's
+            # fp16-rounded w~ by ~2^-12 of the LARGEST term, not of the result)
+            # (+ the fp16 subnormal quantum 2^-24 per element: group 3's outputs sit at the bottom of the fp16 range)
+            assert np.linalg.norm(np64(yk) - wk) <= 1e-3 * np.linalg.norm(wk) + 6e-8 * np.sqrt(wk.size), grp
+
+
 def test_decode_is_deterministic_and_rows_independent():
     N, K, dtype = 14336, 4096, torch.float16
     qw, s, z = gen_layer(N, K, dtype, seed=2, device=DEV)

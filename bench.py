@@ -35,7 +35,7 @@ if ROOT not in sys.path:
 
 LLAMA3_8B = dict(name="Llama-3-8B", hidden=4096, inter=14336, q_heads=32, kv_heads=8, head_dim=128, layers=32)
 LLAMA2_70B = dict(name="Llama-2-70B", hidden=8192, inter=28672, q_heads=64, kv_heads=8, head_dim=128, layers=80)
-METRIC = "Llama-3-8B W4A16 g128 decode tok/s (linear path), 1xB200"
+METRIC = "Llama-3-8B W4A16 g128 decode tok/s (linear path), %dxB200"
 UNIT = "tok/s"
 G = 128
 
@@ -275,6 +275,72 @@ def run_b200(args):
         h2d = sum(v.numel() * 2 for v in hx.values())
         return g, hy, h2d, hy.numel() * 2
 
+    def eager_e2e(M, steps):
+        """The SAME end-to-end step without a CUDA graph: every layer is one eager call of the reference-facing module
+        (the reference's own, unmodified WQLinear.forward when baseline/_ref is staged, else this repo's mirror), as
+        tinychat / awq.entry make them; pinned H2D of the activations and D2H of the result every step."""
+        mods, kind = reference_wqlinears(torch, model, device, dtype)
+        hx = {K: v.cpu().pin_memory() for K, v in make_inputs(M).items()}
+        dx = {K: torch.empty_like(v, device=device).view(1, M, K) for K, v in hx.items()}
+        hy = torch.empty(1, M, cfg["hidden"], dtype=dtype).pin_memory()
+
+        def step():
+            for K in dx:
+                dx[K].copy_(hx[K].view(1, M, K), non_blocking=True)
+            y = None
+            for m, mod in zip(model, mods):
+                y = mod(dx[m["K"]])
+            hy.copy_(y, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            _ = float(hy[0, 0, 0])
+        ms, w = timed_steps(torch, dist, device, step, steps, 5)
+        # host cost of one call when the GPU is not the bottleneck: issue the calls of one step and stop the clock before
+        # waiting for the device
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for m, mod in zip(model, mods):
+            mod(dx[m["K"]])
+        host_us = (time.perf_counter() - t0) * 1e6 / nl
+        torch.cuda.synchronize()
+        return ms / steps, host_us, kind, w
+
+    def batch_sweep():
+        """BASELINE configs[4]: the five Llama-3-8B shapes at M in {1, 4, 16, 64} through the C ABI (the reference
+        dispatch: GEMV entry below 8 tokens, GEMM entry from 8), each shape over its 32 distinct layers (> L2), CUDA
+        graph + events.  us per call and fraction of the HBM roofline (the whole sweep is HBM-bound)."""
+        out = {}
+        shapes = sorted({(m["N"], m["K"]) for m in model})
+        for M in (1, 4, 16, 64):
+            xs = make_inputs(M)
+            row = {}
+            for (N, K) in shapes:
+                layers = [m for m in model if (m["N"], m["K"]) == (N, K)]
+                y = torch.empty(M, N, dtype=dtype, device=device)
+
+                def launch_all():
+                    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+                    for m in layers:
+                        a = (p(xs[K]), p(m["qw"]), p(m["sc"]), p(m["sz"]), p(y), M, N, K, G, 0)
+                        rc = lib.b200awq_w4a16_gemv(*a, st) if M < 8 else lib.b200awq_w4a16_gemm(*a, None, 0, st)
+                        if rc != 0:
+                            raise RuntimeError(lib.b200awq_strerror(rc).decode())
+                s = torch.cuda.Stream()
+                with torch.cuda.stream(s):
+                    launch_all()
+                s.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    launch_all()
+                ms, _ = timed_steps(torch, None, device, g.replay, 20, 3)
+                us = ms * 1e3 / 20 / len(layers)
+                row["%dx%d" % (N, K)] = {"us": round(us, 3), "frac": round(alg_bytes(M, N, K) / us / 1e3 / peaks["hbm"], 4),
+                                         "calls": len(layers)}
+            tot_us = sum(v["us"] * v["calls"] for v in row.values())
+            row["tok_s"] = round(M * 1e6 / tot_us, 1)
+            row["frac"] = round(sum(alg_bytes(M, m["N"], m["K"]) for m in model) / tot_us / 1e3 / peaks["hbm"], 4)
+            out[str(M)] = row
+        return out
+
     sampler.start()
     # ---------------- decode: device-resident
     g_dec, keep1 = abi_graph(1, "gemv")
@@ -303,34 +369,48 @@ def run_b200(args):
         _ = float(hyp[0, 0])
     ms_pe2e, w = timed_steps(torch, dist, device, pe2e_step, ksteps_p, 3)
     windows.append(w)
+    # ---------------- decode end to end WITHOUT a graph (what an unmodified caller sees)
+    ms_eager, host_us, eager_kind, w = eager_e2e(1, min(args.steps, 100))
+    windows.append(w)
+    sweep = batch_sweep() if (world == 1 and args.sweep) else None
     clocks = sampler.stop(windows)
+    tp = None
+    bytes_step = sum(alg_bytes(1, m["N"], m["K"]) for m in model)
+    flops_step = sum(alg_flops(Mp, m["N"], m["K"]) for m in model)
+    weights_bytes = sum(m["qw"].numel() * 2 for m in model)
+    if world > 1:
+        del g_dec, g_e2e, g_pre, g_pe2e, keep1, keep2
+        model.clear()
+        torch.cuda.empty_cache()
+        tp = tp70b_measure(torch, dist, rank, world, device, min(args.steps, 100), args.warmup)
 
     if rank != 0:
         return
     step_ms = ms_dec / args.steps
-    bytes_step = sum(alg_bytes(1, m["N"], m["K"]) for m in model)
     ach = bytes_step / (step_ms * 1e-3) / 1e9
     traffic = None
     tf = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tf):
         traffic = json.load(open(tf)).get("decode_dram_bytes_per_launch")
     pre_ms = ms_pre / ksteps_p
-    flops_step = sum(alg_flops(Mp, m["N"], m["K"]) for m in model)
     tfl = flops_step / (pre_ms * 1e-3) / 1e12
     line = {
-        "metric": METRIC, "value": world * 1000.0 / step_ms, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "metric": METRIC % world, "value": world * 1000.0 / step_ms, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16", "data": "synthetic",
         "config": {"workload": "Llama-3-8B W4A16 g128 decode bs=1: 32 layers x {qkv,o,gate,up,down} GEMV (BASELINE configs[1])",
-                   "launches_per_step": nl, "weights_bytes": sum(m["qw"].numel() * 2 for m in model),
+                   "launches_per_step": nl, "weights_bytes": weights_bytes,
                    "l2": "inputs larger than L2 (3.7 GB of distinct weights per step, model order)",
                    "parallelism": "replicas x%d (model fits one GPU; no collective)" % world, "accumulate": "fp32"},
         "e2e": {"value": world * 1000.0 * args.steps / ms_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps,
                 "api": "awq_inference_engine.gemv_forward_cuda_new x160 in a CUDA graph with the pinned H2D/D2H copies; host sync + read every step"},
+        "e2e_eager": {"value": world * 1000.0 / ms_eager, "unit": UNIT, "ms_per_step": ms_eager, "host_us_per_call": host_us,
+                      "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                      "api": eager_kind + ".forward x160, eager launches (no CUDA graph), pinned H2D/D2H + host read every step"},
         "gpu_launches": nl * args.steps,
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"],
-                     "traffic": traffic, "kernel": "w4a16_stream_kernel", "peak_source": peaks["source"] + " (burst copy)",
+                     "traffic": traffic, "kernel": "w4a16_decode_kernel", "peak_source": peaks["source"] + " (burst copy)",
                      "bytes_per_launch": bytes_step / nl, "avg_launch_us": step_ms * 1e3 / nl},
         "clocks": clocks,
         "prefill": {"metric": "Llama-3-8B W4A16 g128 prefill tok/s (linear path), seq=2048 (BASELINE configs[2])",
@@ -342,24 +422,60 @@ def run_b200(args):
                                  "frac": tfl / peaks["tc_sustained"], "traffic": None, "kernel": "w4a16_umma_kernel",
                                  "peak_source": peaks["source"] + " (sustained cuBLAS bf16)", "frac_of_burst": tfl / peaks["tc_burst"]}},
     }
+    if sweep is not None:
+        line["batch_sweep"] = sweep
+    if tp is not None:
+        line["tp70b"] = tp
+    ptf = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(ptf):
+        line["prefill"]["roofline"]["traffic"] = json.load(open(ptf)).get("prefill_dram_bytes_per_launch")
     if world == 1 and not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(args.cpu_seconds)
     if world == 1 and args.ref_gpu:
         try:
-            line["reference_on_b200"] = reference_gpu(torch, model, make_inputs, device, min(args.steps, 200))
+            line["reference_on_b200"] = reference_gpu(torch, model, make_inputs, device, min(args.steps, 200), lib)
         except Exception as e:  # noqa: BLE001
             line["reference_on_b200"] = {"unavailable": repr(e)[:200]}
     print(json.dumps(line))
 
 
-def run_tp70b(args):
-    """BASELINE configs[3]: Llama-2-70B W4A16 decode bs=1, tensor-parallel over the N ranks of this launch.
-    Per layer and rank: qkv (col) -> o (row, all-reduce) -> gate, up (col) -> down (row, all-reduce); the
-    160 all-reduces of one token are 16 KB each (latency-bound).  Total work is fixed: "strong" scaling."""
-    import torch
+def reference_wqlinears(torch, model, device, dtype):
+    """One reference-facing module per layer of `model`, sharing the layer's packed buffers: the reference's own
+    WQLinear (staged copy under baseline/_ref, see scripts/stage_reference.py) bound to this repo's plugin, else
+    this repo's mirror of it."""
     import llm_awq_b200 as P
-    rank, world, local, dist = dist_setup(torch, args.gpus)
-    device = torch.device("cuda", local)
+    P.engine()
+    staged = os.path.join(ROOT, "baseline", "_ref")
+    cls, kind = None, "llm_awq_b200.WQLinear (mirror of the reference module)"
+    if os.path.exists(os.path.join(staged, "awq", "quantize", "qmodule.py")):
+        try:
+            if staged not in sys.path:
+                sys.path.insert(0, staged)
+            import contextlib
+            with contextlib.redirect_stdout(sys.stderr):   # the reference prints notices at import: stdout is the JSON line's
+                from awq.quantize.qmodule import WQLinear as RefWQLinear
+            cls, kind = RefWQLinear, "reference awq.quantize.qmodule.WQLinear (unmodified, baseline/_ref) on this plugin"
+        except Exception:  # noqa: BLE001
+            cls = None
+    mods = []
+    for m in model:
+        if cls is not None:
+            mod = cls(4, G, 128, 8, False, "cpu", dtype=dtype)   # tiny buffers, replaced below
+            mod.in_features, mod.out_features = m["K"], m["N"]
+        else:
+            mod = P.WQLinear(4, G, 128, 8, False, "cpu")
+            mod.in_features, mod.out_features = m["K"], m["N"]
+        mod.qweight, mod.scales, mod.scaled_zeros = m["qw"], m["sc"], m["sz"]
+        mods.append(mod)
+    return mods, kind
+
+
+def tp70b_measure(torch, dist, rank, world, device, steps, warmup):
+    """BASELINE configs[3]: Llama-2-70B W4A16 decode bs=1, tensor-parallel over the ranks of this launch.
+    Per layer and rank: qkv (col) -> o (row, all-reduce) -> gate, up (col) -> down (row, all-reduce); the
+    160 all-reduces of one token are 16 KB each (latency-bound).  Total work is fixed: "strong" scaling.
+    Returns the record (rank 0) or None."""
+    import llm_awq_b200 as P
     dtype = torch.float16
     lib = P.lib()
     cfg = LLAMA2_70B
@@ -399,32 +515,40 @@ def run_tp70b(args):
         with torch.cuda.graph(g):
             step(mode)
         return g
-    ms_nc, _ = timed_steps(torch, dist, device, graph("none").replay, args.steps, args.warmup)
+    ms_nc, _ = timed_steps(torch, dist, device, graph("none").replay, steps, warmup)
     ms_nccl = ms_fused = None
     if world > 1:
-        ms_nccl, _ = timed_steps(torch, dist, device, graph("nccl").replay, args.steps, args.warmup)
-        ms_fused, _ = timed_steps(torch, dist, device, graph("fused").replay, args.steps, args.warmup)
+        ms_nccl, _ = timed_steps(torch, dist, device, graph("nccl").replay, steps, warmup)
+        ms_fused, _ = timed_steps(torch, dist, device, graph("fused").replay, steps, warmup)
     ms_full = ms_nc if world == 1 else min(ms_nccl, ms_fused)
     if rank != 0:
-        return
-    step_ms = ms_full / args.steps
+        return None
+    step_ms = ms_full / steps
     bytes_rank = sum(alg_bytes(1, m["N"], m["K"]) for m in model)
-    print(json.dumps({
+    return {
         "metric": "Llama-2-70B W4A16 g128 decode tok/s (linear path), TP=%d" % world, "value": 1000.0 / step_ms, "unit": UNIT,
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True,
+        "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": step_ms, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
         "config": {"workload": "Llama-2-70B W4A16 g128 decode bs=1, TP=%d (BASELINE configs[3])" % world,
                    "parallelism": "tp%d: column-parallel qkv/gate/up, row-parallel o/down + 1 all-reduce each (NCCL, or fused into the GEMV over NVLink peer memory)" % world,
                    "launches_per_step": len(model), "allreduces_per_step": 0 if world == 1 else 2 * cfg["layers"],
                    "allreduce_bytes": cfg["hidden"] * 2, "l2": "inputs larger than L2"},
-        "comm": {"ms_per_step_without_allreduce": ms_nc / args.steps,
-                 "ms_per_step_nccl_allreduce": None if ms_nccl is None else ms_nccl / args.steps,
-                 "ms_per_step_fused_nvlink_exchange": None if ms_fused is None else ms_fused / args.steps,
+        "comm": {"ms_per_step_without_allreduce": ms_nc / steps,
+                 "ms_per_step_nccl_allreduce": None if ms_nccl is None else ms_nccl / steps,
+                 "ms_per_step_fused_nvlink_exchange": None if ms_fused is None else ms_fused / steps,
                  "headline_uses": "single GPU" if world == 1 else ("fused" if ms_fused <= ms_nccl else "nccl")},
-        "gpu_launches": len(model) * args.steps,
+        "gpu_launches": len(model) * steps,
         "roofline": {"bound": "hbm", "achieved": bytes_rank / (step_ms * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
                      "frac": bytes_rank / (step_ms * 1e-3) / 1e9 / peaks["hbm"], "traffic": None, "per": "rank",
-                     "frac_without_allreduce": bytes_rank / (ms_nc / args.steps * 1e-3) / 1e9 / peaks["hbm"]}}))
+                     "frac_without_allreduce": bytes_rank / (ms_nc / steps * 1e-3) / 1e9 / peaks["hbm"]}}
+
+
+def run_tp70b(args):
+    import torch
+    rank, world, local, dist = dist_setup(torch, args.gpus)
+    rec = tp70b_measure(torch, dist, rank, world, torch.device("cuda", local), args.steps, args.warmup)
+    if rec is not None:
+        print(json.dumps(rec))
 
 
 def cpu_layer(torch, layers=1):
@@ -471,21 +595,45 @@ def cpu_baseline(budget_s=15.0):
         step()
         ts.append(time.time() - t0)
     med = statistics.median(ts)
-    return {"value": 1.0 / (med * LLAMA3_8B["layers"]), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+    return {"value": 1.0 / (med * LLAMA3_8B["layers"]), "unit": UNIT, "cores": torch.get_num_threads(),
+            "host_cores": os.cpu_count(), "kind": "port",
             "sample": "1 of 32 decoder layers (5 WQLinear forwards, M=1, dequant every call, fp32 torch ops), %d repeats, median; "
                       "tok/s = 1 / (32 x layer time)" % len(ts)}
 
 
-def reference_gpu(torch, model, make_inputs, device, steps):
-    """The reference's own CUDA kernels (oracle/_ref: unmodified sources rebuilt for sm_100a) through
-    their own entry points, plain launches on the legacy default stream (they cannot be graph-captured)."""
+def kernel_only_ms(torch, step):
+    """Sum of the DEVICE durations of the kernels one step launches (CUPTI through torch.profiler): the time the GPU
+    spends inside the kernels, without launch gaps.  None when the profiler is unavailable."""
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        step()
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            step()
+            torch.cuda.synchronize()
+        tot = 0.0
+        for e in prof.key_averages():
+            if "memcpy" in e.key.lower() or "memset" in e.key.lower():
+                continue
+            tot += float(getattr(e, "device_time_total", getattr(e, "cuda_time_total", 0.0)))
+        return tot / 1e3 if tot > 0 else None
+    except Exception:  # noqa: BLE001
+        return None
+
+
+def reference_gpu(torch, model, make_inputs, device, steps, lib=None):
+    """The reference's own CUDA kernels (oracle/_ref: unmodified sources rebuilt for sm_100a) through their own entry
+    points: plain launches on the legacy default stream (they cannot be graph-captured), and the kernel-only device
+    time of the same step.  With `lib`, this repo's C ABI is timed in the SAME two modes beside it."""
     d = os.path.join(ROOT, "oracle", "_ref")
     sys.path.insert(0, d)
     import importlib
     ref = importlib.import_module("ref_awq_engine")
     out = {}
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
     for tag, M, k in (("decode", 1, steps), ("prefill", 2048, 5)):
         xs = make_inputs(M, 0.25)
+        ys = {N: torch.empty(M, N, dtype=torch.float16, device=device) for N in {m["N"] for m in model}}
 
         def step():
             for m in model:
@@ -493,10 +641,36 @@ def reference_gpu(torch, model, make_inputs, device, steps):
                     ref.gemv_forward_cuda_new(xs[m["K"]], m["qw"], m["sc"], m["sz"], M, m["N"], m["K"], G)
                 else:
                     ref.gemm_forward_cuda_new(xs[m["K"]], m["qw"], m["sc"], m["sz"])
+
+        def ours():
+            st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+            for m in model:
+                a = (p(xs[m["K"]]), p(m["qw"]), p(m["sc"]), p(m["sz"]), p(ys[m["N"]]), M, m["N"], m["K"], G, 0)
+                rc = lib.b200awq_w4a16_gemv(*a, st) if M < 8 else lib.b200awq_w4a16_gemm(*a, None, 0, st)
+                if rc != 0:
+                    raise RuntimeError(lib.b200awq_strerror(rc).decode())
         with torch.cuda.stream(torch.cuda.default_stream()):
             ms, _ = timed_steps(torch, None, device, step, k, 3)
-        out[tag] = {"value": M * 1000.0 * k / ms, "unit": UNIT, "ms_per_step": ms / k, "steps": k}
-    out["how"] = "ref_awq_engine.{gemv,gemm}_forward_cuda_new, 160 calls per step, plain launches, CUDA events"
+            ko = kernel_only_ms(torch, step)
+        out[tag] = {"value": M * 1000.0 * k / ms, "unit": UNIT, "ms_per_step": ms / k, "steps": k,
+                    "eager": {"value": M * 1000.0 * k / ms, "ms_per_step": ms / k},
+                    "kernel_only": None if ko is None else {"value": M * 1000.0 / ko, "ms_per_step": ko}}
+        if lib is not None:
+            ms_o, _ = timed_steps(torch, None, device, ours, k, 3)
+            # kernel-only needs non-overlapping kernels: with programmatic dependent launch a kernel's device duration
+            # includes the time it spends prefetching under its predecessor, so the durations are summed with PDL off
+            prev = lib.b200awq_set_pdl(0)
+            ms_np, _ = timed_steps(torch, None, device, ours, k, 3)
+            ko_o = kernel_only_ms(torch, ours)
+            lib.b200awq_set_pdl(prev)
+            out[tag]["this_repo_same_modes"] = {
+                "eager": {"value": M * 1000.0 * k / ms_o, "ms_per_step": ms_o / k},
+                "eager_pdl_off": {"value": M * 1000.0 * k / ms_np, "ms_per_step": ms_np / k},
+                "kernel_only_pdl_off": None if ko_o is None else {"value": M * 1000.0 / ko_o, "ms_per_step": ko_o}}
+    out["how"] = ("ref_awq_engine.{gemv,gemm}_forward_cuda_new, 160 calls per step: `eager` = plain launches timed with CUDA "
+                  "events, `kernel_only` = sum of kernel device durations (CUPTI); this_repo_same_modes = this repo's C ABI "
+                  "in the same modes (plain launches, no CUDA graph; kernel-only with programmatic dependent launch off, because overlapped "
+                  "kernels' durations cannot be summed)")
     return out
 
 
@@ -518,12 +692,13 @@ def run_reference(args):
     v = 1.0 / (dt * LLAMA3_8B["layers"])
     sample = "each step = 1 of 32 decoder layers (5 WQLinear forwards, M=1, dequant every call); tok/s = 1/(32 x step time)"
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": max(args.warmup, 1),
+        "impl": "reference", "metric": METRIC % 1, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": max(args.warmup, 1),
         "ms_per_step": dt * 1e3, "steps_per_token": LLAMA3_8B["layers"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32",
         "data": "synthetic", "config": {"workload": "Llama-3-8B W4A16 g128 decode bs=1 (BASELINE configs[1]), CPU pure-PyTorch dequant path",
                                         "sample": sample},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "host_cores": os.cpu_count(), "kind": "port",
+                         "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
 
 
@@ -539,7 +714,7 @@ def run_reference_gpu(args):
         g = torch.Generator(device=device).manual_seed(99 + M)
         return {K: (torch.randn(M, K, generator=g, device=device) * scale).to(torch.float16) for K in (4096, 14336)}
     r = reference_gpu(torch, model, make_inputs, device, min(args.steps, 200))
-    print(json.dumps({"impl": "reference-gpu", "metric": METRIC, "value": r["decode"]["value"], "unit": UNIT, "n_gpus": 1,
+    print(json.dumps({"impl": "reference-gpu", "metric": METRIC % 1, "value": r["decode"]["value"], "unit": UNIT, "n_gpus": 1,
                       "higher_is_better": True, "detail": r}))
 
 
@@ -554,6 +729,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=30)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-ref-gpu", dest="ref_gpu", action="store_false")
+    ap.add_argument("--no-sweep", dest="sweep", action="store_false")
     ap.add_argument("--workload", default="llama3", choices=["llama3", "tp70b"])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

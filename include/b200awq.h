@@ -94,6 +94,21 @@ int b200awq_w4a16_gemv_allreduce(const void* x, const void* qweight, const void*
                                  void* y, int m, int n, int k, int group_size, int dtype,
                                  const b200awq_peers* peers, void* stream);
 
+/* Front half of the gated MLP: y = silu(x Wgate~^T) * (x Wup~^T), i.e. what
+ * QuantLlamaMLP.our_llama_mlp computes with two engine calls, F.silu and a multiply
+ *   reference: tinychat/modules/fused_mlp.py:36-83 (both branches use the zeros tensor they are GIVEN; the GEMM
+ *   branch's `scaled_zeros - 8 * scales` is the caller's business).
+ * Same tensor layouts as b200awq_w4a16_gemv / gemm for each weight set; y is [m, n].  Roundings are the reference's:
+ * gate and up products rounded to T, silu (fp32) rounded to T, product rounded to T.
+ *   m == 1, fp16: ONE kernel -- x read once, the two weight streams share one shared-memory ring, one [1, n] write
+ *                 (no workspace needed).
+ *   otherwise:    the two products through the GEMV / GEMM path into `workspace` (>= b200awq_w4a16_mlp_front_workspace_bytes
+ *                 = 2 * m * n * 2 bytes, 16-byte aligned), then one elementwise kernel.  n % 128 == 0 for m >= 8. */
+int b200awq_w4a16_mlp_front(const void* x, const void* gate_qweight, const void* gate_scales, const void* gate_szeros,
+                            const void* up_qweight, const void* up_scales, const void* up_szeros, void* y, int m, int n, int k,
+                            int group_size, int dtype, void* workspace, size_t workspace_bytes, void* stream);
+size_t b200awq_w4a16_mlp_front_workspace_bytes(int m, int n, int k);
+
 /* RMSNorm of the decoder layers around the quantised linears: y[i, :] = x[i, :] *
  * rsqrt(mean(x[i, :]^2) + eps) * gamma, statistics in fp32, one rounding to the element type (fp16 results are
  * clamped to +-(65504 - 1000) like the reference).  Replaces layernorm_forward_cuda(input, gamma, out, eps)

@@ -87,6 +87,46 @@ torch::Tensor gemm_forward_cuda_new(torch::Tensor _in_feats, torch::Tensor _kern
   return out;
 }
 
+// New entry (no counterpart in the reference's extension): the whole of QuantLlamaMLP.our_llama_mlp
+// (tinychat/modules/fused_mlp.py:36-83) in one call.  The zeros tensors are used as given.
+torch::Tensor mlp_front_forward_cuda(torch::Tensor _in_feats, torch::Tensor _gate_kernel, torch::Tensor _gate_scales,
+                                     torch::Tensor _gate_zeros, torch::Tensor _up_kernel, torch::Tensor _up_scales,
+                                     torch::Tensor _up_zeros) {
+  check_inputs(_in_feats, _gate_kernel, _gate_scales, _gate_zeros);
+  check_inputs(_in_feats, _up_kernel, _up_scales, _up_zeros);
+  const int dt = dtype_code(_in_feats, "mlp_front_forward_cuda");
+  const int64_t k = _in_feats.size(-1);
+  const int64_t n = _gate_kernel.size(0) * 4;
+  const int64_t m = _in_feats.numel() / k;
+  TORCH_CHECK(_gate_kernel.size(1) == k && _up_kernel.size(0) * 4 == n && _up_kernel.size(1) == k, "qweights do not match");
+  for (const torch::Tensor* t : {&_gate_scales, &_gate_zeros, &_up_scales, &_up_zeros})
+    TORCH_CHECK(t->size(1) == n && t->size(0) * 128 >= k, "scales / zeros do not match (n, k)");
+  const c10::cuda::CUDAGuard guard(_in_feats.device());
+  std::vector<int64_t> output_shape = _in_feats.sizes().vec();
+  output_shape.back() = n;
+  at::Tensor out = torch::empty(output_shape, _in_feats.options());
+  if (m == 0) return out;
+  at::Tensor ws;
+  size_t ws_bytes = 0;
+  if (!(m == 1 && dt == B200AWQ_DTYPE_F16)) {
+    ws_bytes = b200awq_w4a16_mlp_front_workspace_bytes((int)m, (int)n, (int)k);
+    ws = torch::empty({(int64_t)ws_bytes}, _in_feats.options().dtype(torch::kUInt8));
+  }
+  int rc = b200awq_w4a16_mlp_front(_in_feats.data_ptr(), _gate_kernel.data_ptr(), _gate_scales.data_ptr(), _gate_zeros.data_ptr(),
+                                   _up_kernel.data_ptr(), _up_scales.data_ptr(), _up_zeros.data_ptr(), out.data_ptr(), (int)m,
+                                   (int)n, (int)k, 128, dt, ws_bytes ? ws.data_ptr() : nullptr, ws_bytes,
+                                   at::cuda::getCurrentCUDAStream().stream());
+  if (rc == B200AWQ_ERR_WORKSPACE && ws_bytes == 0) {  // the one-kernel path declined the shape: composed path
+    ws_bytes = b200awq_w4a16_mlp_front_workspace_bytes((int)m, (int)n, (int)k);
+    ws = torch::empty({(int64_t)ws_bytes}, _in_feats.options().dtype(torch::kUInt8));
+    rc = b200awq_w4a16_mlp_front(_in_feats.data_ptr(), _gate_kernel.data_ptr(), _gate_scales.data_ptr(), _gate_zeros.data_ptr(),
+                                 _up_kernel.data_ptr(), _up_scales.data_ptr(), _up_zeros.data_ptr(), out.data_ptr(), (int)m, (int)n,
+                                 (int)k, 128, dt, ws.data_ptr(), ws_bytes, at::cuda::getCurrentCUDAStream().stream());
+  }
+  raise(rc, false);
+  return out;
+}
+
 // reference: awq/kernels/csrc/layernorm/layernorm.cu:111-131 (input [b, s, c], gamma [c], out like input; returns
 // nothing).  Same dtype checks; additionally any rank >= 1 is accepted (rows = numel / last dim), the launch goes to
 // the current stream, and contiguity is checked instead of assumed.
@@ -111,6 +151,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gemm_forward_cuda_new", &gemm_forward_cuda_new, "New quantized GEMM kernel.");
   m.def("gemv_forward_cuda_new", &gemv_forward_cuda_new, "New quantized GEMV kernel.");
   m.def("layernorm_forward_cuda", &layernorm_forward_cuda, "FasterTransformer layernorm kernel");
+  m.def("mlp_front_forward_cuda", &mlp_front_forward_cuda, "silu(x Wgate^T) * (x Wup^T) for W4A16 weights, one call");
   m.def("set_pdl", [](bool on) { return b200awq_set_pdl(on ? 1 : 0) != 0; }, "programmatic dependent launch on/off");
   m.def("launch_count", []() { return b200awq_launch_count(); }, "kernels launched by libb200awq so far");
   m.def("version", []() { return std::string(b200awq_version()); });

@@ -93,6 +93,9 @@ struct DecArgs {
   const uint16_t* qw;
   const void* sc;
   const void* sz;
+  const uint16_t* qw2;  // FUSED (gate + up + SiLU * mul): the second weight set (up projection); the first one is the gate
+  const void* sc2;
+  const void* sz2;
   void* y;
   int N, K;
   int S;        // CTAs per cluster = k split
@@ -136,10 +139,23 @@ __device__ __forceinline__ void dec_imma(int (&d)[4], uint32_t a0, uint32_t a1, 
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]));
 }
 
-template <typename T, int CONS>
+// silu(g) * u with the reference's roundings (tinychat/modules/fused_mlp.py:40-60,80: gate and up outputs are tensors
+// of T, F.silu rounds to T, the product rounds to T)
+template <typename T>
+__device__ __forceinline__ T silu_mul_rounded(float gate_acc, float up_acc) {
+  const float g = (float)from_float<T>(gate_acc), u = (float)from_float<T>(up_acc);
+  const float s = (float)from_float<T>(g / (1.f + expf(-g)));
+  return from_float<T>(s * u);
+}
+
+// FUSED = false: y = x W~^T.   FUSED = true: y = silu(x Wgate~^T) * (x Wup~^T), both weight sets walked row block by row
+// block through the same ring (one read of x, two weight streams, one [1, n] write).
+template <typename T, int CONS, bool FUSED>
 __global__ void __launch_bounds__((CONS + 2) * 32, 2) w4a16_decode_kernel(const __grid_constant__ DecArgs a) {
   constexpr bool kBf16 = TypeTraits<T>::kIsBf16;
   constexpr int kDecCons = CONS;
+  constexpr int NT = FUSED ? 2 : 1;   // weight sets
+  constexpr int RW = 16 * NT;         // partial sums per row block and warp
   constexpr int kBatch = CONS == 8 ? 2 : 1;  // groups whose loads are issued together
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -188,7 +204,7 @@ __global__ void __launch_bounds__((CONS + 2) * 32, 2) w4a16_decode_kernel(const 
       for (int rb = lane; rb < nrb; rb += 32) {
         const int nch = min(16, (nq - 4 * rb) * 4);
         mbar_init(&xch[rb], 1);
-        mbar_expect_tx(&xch[rb], (uint32_t)(nch * 4 * (S - 1)));
+        mbar_expect_tx(&xch[rb], (uint32_t)(nch * 4 * NT * (S - 1)));
       }
     }
     mbar_fence_init();
@@ -208,7 +224,12 @@ __global__ void __launch_bounds__((CONS + 2) * 32, 2) w4a16_decode_kernel(const 
 #endif
     for (int rb = 0; rb < nrb; ++rb) {
       const int qb = q_lo + 4 * rb, nqb = min(4, q_hi - qb);  // quad rows of this row block
-      for (int p = 0; p < npc; ++p) {
+      for (int pt = 0; pt < npc * NT; ++pt) {
+        const int p = FUSED ? (pt >= npc ? pt - npc : pt) : pt;
+        const bool second = FUSED && pt >= npc;
+        const uint16_t* qwt = second ? a.qw2 : a.qw;
+        const uint8_t* sct = second ? reinterpret_cast<const uint8_t*>(a.sc2) : scb;
+        const uint8_t* szt = second ? reinterpret_cast<const uint8_t*>(a.sz2) : szb;
         const int g0 = kg_lo + p * kDecPiece, ng = min(kDecPiece, kg_hi - g0);
         for (int h = 0; h < nqb; h += 2) {  // one slot per octet
           DEC_CLK(t0);
@@ -227,17 +248,17 @@ __global__ void __launch_bounds__((CONS + 2) * 32, 2) w4a16_decode_kernel(const 
           const uint32_t len = (uint32_t)ng * 256u;
           if (lane == 0) {
             mbar_expect_tx(&full[slot], (uint32_t)nqs * len);
-            bulk_g2s(sw, a.qw + (size_t)q0 * K + (size_t)g0 * kGroup, len, &full[slot]);
-            if (nqs > 1) bulk_g2s(sw + kDecQuadB, a.qw + (size_t)(q0 + 1) * K + (size_t)g0 * kGroup, len, &full[slot]);
+            bulk_g2s(sw, qwt + (size_t)q0 * K + (size_t)g0 * kGroup, len, &full[slot]);
+            if (nqs > 1) bulk_g2s(sw + kDecQuadB, qwt + (size_t)(q0 + 1) * K + (size_t)g0 * kGroup, len, &full[slot]);
           }
           if (lane < ng) {  // lane = group: 8 bytes (4 channels) of scales and of zeros per quad row
             const size_t off = ((size_t)(g0 + lane) * N + (size_t)q0 * 4) * 2;
             const uint32_t dst = smem_u32(sw) + kDecScaleOff + lane * 8;
-            dec_cp_async8(dst, scb + off);
-            dec_cp_async8(dst + kDecPiece * 8, szb + off);
+            dec_cp_async8(dst, sct + off);
+            dec_cp_async8(dst + kDecPiece * 8, szt + off);
             if (nqs > 1) {
-              dec_cp_async8(dst + 2 * kDecPiece * 8, scb + off + 8);
-              dec_cp_async8(dst + 3 * kDecPiece * 8, szb + off + 8);
+              dec_cp_async8(dst + 2 * kDecPiece * 8, sct + off + 8);
+              dec_cp_async8(dst + 3 * kDecPiece * 8, szt + off + 8);
             }
           }
           dec_cp_async_arrive(&full[slot]);
@@ -277,39 +298,53 @@ __global__ void __launch_bounds__((CONS + 2) * 32, 2) w4a16_decode_kernel(const 
     // cluster, ranks > 0 push their sums into rank 0's shared memory (st.async completing bytes on rank 0's mbarrier);
     // rank 0 parks its own sums and completes row blocks (add the peers', round, store) as their words arrive.
     T* y = reinterpret_cast<T*>(a.y);
-    float* hold = xchg + (S - 1) * a.nrb_max * 16;  // [row block][16 ch]: rank 0's own sums until the peers' arrive
+    float* hold = xchg + (S - 1) * a.nrb_max * RW;  // [row block][RW]: rank 0's own sums until the peers' arrive
     const int ch = lane & 15;
+    const bool mine = lane < RW;  // lanes 0-15: channels of the (gate) product, lanes 16-31: of the up product (FUSED)
+    // final value of channel `ch` from the summed accumulators of this lane (FUSED: lane ch holds the gate sum, lane
+    // 16 + ch the up sum) and its store
+    auto finish = [&](float v, int n0, int nch) {
+      if (FUSED) {
+        const float up = __shfl_down_sync(0xffffffffu, v, 16);
+        if (lane < nch) y[n0 + ch] = silu_mul_rounded<T>(v, up);
+      } else {
+        if (lane < nch) y[n0 + ch] = from_float<T>(v);
+      }
+    };
     int fl = 0;  // rank 0, k split: next row block to complete
     for (int rb = 0; rb < nrb; ++rb) {
       const int rs = rb % kDecRed;
       mbar_wait(&rbfull[rs], (uint32_t)((rb / kDecRed) & 1));
       float v = 0.f;
+      if (mine) {
 #pragma unroll
-      for (int w = 0; w < kDecCons; ++w) v += red[(rs * kDecCons + w) * 16 + ch];  // fixed order: deterministic
+        for (int w = 0; w < kDecCons; ++w) v += red[(rs * kDecCons + w) * RW + lane];  // fixed order: deterministic
+      }
       __syncwarp();
       if (lane == 0) mbar_arrive(&rbfree[rs]);
       const int n0 = (q_lo + 4 * rb) * 4, nch = min(16, (nq - 4 * rb) * 4);
       if (S == 1) {
-        if (lane < nch) y[n0 + ch] = from_float<T>(v);
+        finish(v, n0, nch);
       } else if (rank > 0) {
-        if (lane < nch) {
+        if (mine && ch < nch) {
           const uint32_t dbar = map_to_rank(smem_u32(&xch[rb]), 0);
-          const uint32_t dst = map_to_rank(smem_u32(&xchg[((rank - 1) * a.nrb_max + rb) * 16 + ch]), 0);
+          const uint32_t dst = map_to_rank(smem_u32(&xchg[((rank - 1) * a.nrb_max + rb) * RW + lane]), 0);
           asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(dst),
                        "r"(__float_as_uint(v)), "r"(dbar)
                        : "memory");
         }
       } else {
-        if (lane < 16) hold[rb * 16 + ch] = v;  // read back by the same lane only
+        if (mine) hold[rb * RW + lane] = v;  // read back by the same lane only
         while (fl <= rb) {
           const bool ok = __all_sync(0xffffffffu, mbar_try_wait(&xch[fl], 0));
           if (!ok) break;
           const int f0 = (q_lo + 4 * fl) * 4, fch = min(16, (nq - 4 * fl) * 4);
-          if (lane < fch) {
-            float r = hold[fl * 16 + ch];
-            for (int pr = 0; pr < S - 1; ++pr) r += xchg[(pr * a.nrb_max + fl) * 16 + ch];  // fixed order
-            y[f0 + ch] = from_float<T>(r);
+          float r = 0.f;
+          if (mine && ch < fch) {
+            r = hold[fl * RW + lane];
+            for (int pr = 0; pr < S - 1; ++pr) r += xchg[(pr * a.nrb_max + fl) * RW + lane];  // fixed order
           }
+          finish(r, f0, fch);
           ++fl;
         }
       }
@@ -318,11 +353,12 @@ __global__ void __launch_bounds__((CONS + 2) * 32, 2) w4a16_decode_kernel(const 
       for (; fl < nrb; ++fl) {
         mbar_wait(&xch[fl], 0);
         const int f0 = (q_lo + 4 * fl) * 4, fch = min(16, (nq - 4 * fl) * 4);
-        if (lane < fch) {
-          float r = hold[fl * 16 + ch];
-          for (int pr = 0; pr < S - 1; ++pr) r += xchg[(pr * a.nrb_max + fl) * 16 + ch];
-          y[f0 + ch] = from_float<T>(r);
+        float r = 0.f;
+        if (mine && ch < fch) {
+          r = hold[fl * RW + lane];
+          for (int pr = 0; pr < S - 1; ++pr) r += xchg[(pr * a.nrb_max + fl) * RW + lane];
         }
+        finish(r, f0, fch);
       }
     }
     DEC_STAMP(6);
@@ -431,8 +467,10 @@ __global__ void __launch_bounds__((CONS + 2) * 32, 2) w4a16_decode_kernel(const 
   for (int rb = 0; rb < nrb; ++rb) {
     const int nqb = min(4, nq - 4 * rb);
     const bool two = nqb > 2;  // second octet present
-    float y0 = 0.f, y1 = 0.f;
-    for (int p = 0; p < npc; ++p) {
+    float y0 = 0.f, y1 = 0.f, yg0 = 0.f, yg1 = 0.f;  // FUSED: yg* park the gate sums while the up weights stream
+    for (int pt = 0; pt < npc * NT; ++pt) {
+      const int p = FUSED ? (pt >= npc ? pt - npc : pt) : pt;
+      if (FUSED && pt == npc) yg0 = y0, yg1 = y1, y0 = 0.f, y1 = 0.f;
       const int ng = min(kDecPiece, ngr - p * kDecPiece);
       int slotB = slot, useB = use;
       if (two && ++slotB == NS) slotB = 0, ++useB;
@@ -501,12 +539,23 @@ __global__ void __launch_bounds__((CONS + 2) * 32, 2) w4a16_decode_kernel(const 
     y1 += __shfl_xor_sync(0xffffffffu, y1, 1);
     y0 += __shfl_xor_sync(0xffffffffu, y0, 2);
     y1 += __shfl_xor_sync(0xffffffffu, y1, 2);
+    if (FUSED) {
+      yg0 += __shfl_xor_sync(0xffffffffu, yg0, 1);
+      yg1 += __shfl_xor_sync(0xffffffffu, yg1, 1);
+      yg0 += __shfl_xor_sync(0xffffffffu, yg0, 2);
+      yg1 += __shfl_xor_sync(0xffffffffu, yg1, 2);
+    }
     const int rs = rb % kDecRed;
     if (rb >= kDecRed) mbar_wait(&rbfree[rs], (uint32_t)((rb / kDecRed - 1) & 1));
     if (tig == 0) {
-      float* r = red + (rs * kDecCons + warp) * 16;
-      r[c] = y0;
-      r[c + 8] = y1;
+      float* r = red + (rs * kDecCons + warp) * RW;
+      if (FUSED) {
+        r[c] = yg0, r[c + 8] = yg1;   // gate
+        r[16 + c] = y0, r[24 + c] = y1;  // up
+      } else {
+        r[c] = y0;
+        r[c + 8] = y1;
+      }
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&rbfull[rs]);
@@ -540,14 +589,18 @@ int next_dec_seq() {
 
 }  // namespace
 
-int launch_decode(const void* x, const void* qw, const void* sc, const void* sz, void* y, int N, int K, int dtype, bool pdl,
-                  const DecodeTuning& tune, cudaStream_t stream) {
+namespace {
+int launch_decode_impl(const void* x, const void* qw, const void* sc, const void* sz, const void* qw2, const void* sc2,
+                       const void* sz2, void* y, int N, int K, int dtype, bool pdl, const DecodeTuning& tune, cudaStream_t stream) {
+  const bool fused = qw2 != nullptr;
+  const int nt = fused ? 2 : 1;
   if (N % 8 || K % kGroup) return B200AWQ_ERR_SHAPE;
   const int nsm = dec_sm_count();
   if (nsm < 1) return B200AWQ_ERR_SHAPE;
   const int G = K / kGroup, Q = N / 4;
   DecArgs a{};
   a.x = x, a.qw = static_cast<const uint16_t*>(qw), a.sc = sc, a.sz = sz, a.y = y;
+  a.qw2 = static_cast<const uint16_t*>(qw2), a.sc2 = sc2, a.sz2 = sz2;
   a.N = N, a.K = K;
   // k split: only when the rows alone cannot balance the SMs (efficiency of dealing Q quad rows to nsm CTAs below
   // ~0.9) and the halves still make copies of >= 4 KB; or when the digits of the whole k range would crowd out the ring
@@ -579,8 +632,8 @@ int launch_decode(const void* x, const void* qw, const void* sc, const void* sz,
   L.x = off, off += ngr * kDecGroupBytes;
   L.gx = off, off += ngr * 4 * 8;
   const int cons = tune.warps == 8 ? 8 : 16;
-  L.red = off, off += kDecRed * cons * 16 * 4;
-  L.xchg = off, off += S * nrb_max * 16 * 4;  // the peers' sums (S - 1 regions) + rank 0's own parked sums
+  L.red = off, off += kDecRed * cons * 16 * nt * 4;
+  L.xchg = off, off += S * nrb_max * 16 * nt * 4;  // the peers' sums (S - 1 regions) + rank 0's own parked sums
   off = (off + 127) & ~127;
   L.ring = off;
   int ns = (kDecSmemBudget - off) / kDecSlotBytes;
@@ -590,18 +643,22 @@ int launch_decode(const void* x, const void* qw, const void* sc, const void* sz,
   a.NS = ns;
   L.total = off + ns * kDecSlotBytes;
 
-  static bool attr_set[2][2][32] = {};
+  static bool attr_set[2][2][2][32] = {};
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return B200AWQ_ERR_DEVICE;
   const int ti = dtype == B200AWQ_DTYPE_F16 ? 0 : 1;
   const int ci = cons == 8 ? 0 : 1;
-  const void* kerns[2][2] = {{(const void*)w4a16_decode_kernel<__half, 8>, (const void*)w4a16_decode_kernel<__half, 16>},
-                             {(const void*)w4a16_decode_kernel<__nv_bfloat16, 8>, (const void*)w4a16_decode_kernel<__nv_bfloat16, 16>}};
-  const void* kern = kerns[ti][ci];
-  if (!attr_set[ti][ci][dev & 31]) {
+  const int fi = fused ? 1 : 0;
+  const void* kerns[2][2][2] = {
+      {{(const void*)w4a16_decode_kernel<__half, 8, false>, (const void*)w4a16_decode_kernel<__half, 8, true>},
+       {(const void*)w4a16_decode_kernel<__half, 16, false>, (const void*)w4a16_decode_kernel<__half, 16, true>}},
+      {{(const void*)w4a16_decode_kernel<__nv_bfloat16, 8, false>, (const void*)w4a16_decode_kernel<__nv_bfloat16, 8, true>},
+       {(const void*)w4a16_decode_kernel<__nv_bfloat16, 16, false>, (const void*)w4a16_decode_kernel<__nv_bfloat16, 16, true>}}};
+  const void* kern = kerns[ti][ci][fi];
+  if (!attr_set[ti][ci][fi][dev & 31]) {
     if (cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecSmemBudget)) return (int)e;
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    attr_set[ti][ci][dev & 31] = true;
+    attr_set[ti][ci][fi][dev & 31] = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(a.units * a.S));
@@ -627,6 +684,19 @@ int launch_decode(const void* x, const void* qw, const void* sc, const void* sz,
   void* args[] = {const_cast<DecArgs*>(&a)};
   cudaError_t e = cudaLaunchKernelExC(&cfg, kern, args);
   return e == cudaSuccess ? 0 : (int)e;
+}
+}  // namespace
+
+int launch_decode(const void* x, const void* qw, const void* sc, const void* sz, void* y, int N, int K, int dtype, bool pdl,
+                  const DecodeTuning& tune, cudaStream_t stream) {
+  return launch_decode_impl(x, qw, sc, sz, nullptr, nullptr, nullptr, y, N, K, dtype, pdl, tune, stream);
+}
+
+int launch_decode_mlp_front(const void* x, const void* gqw, const void* gsc, const void* gsz, const void* uqw, const void* usc,
+                            const void* usz, void* y, int N, int K, int dtype, bool pdl, const DecodeTuning& tune,
+                            cudaStream_t stream) {
+  if (!uqw || !usc || !usz) return B200AWQ_ERR_ALIGN;
+  return launch_decode_impl(x, gqw, gsc, gsz, uqw, usc, usz, y, N, K, dtype, pdl, tune, stream);
 }
 
 }  // namespace b200awq

@@ -80,6 +80,14 @@ struct DecodeTuning {
 int launch_decode(const void* x, const void* qw, const void* sc, const void* sz, void* y, int N, int K, int dtype, bool pdl,
                   const DecodeTuning& tune, cudaStream_t stream);
 
+// one-token fused MLP front half: y = silu(x Wgate~^T) * (x Wup~^T), both weight sets through one ring (w4a16_decode.cu)
+int launch_decode_mlp_front(const void* x, const void* gqw, const void* gsc, const void* gsz, const void* uqw, const void* usc,
+                            const void* usz, void* y, int N, int K, int dtype, bool pdl, const DecodeTuning& tune,
+                            cudaStream_t stream);
+
+// out = silu(gate) * up over `count` elements, the reference's roundings (silu_mul.cu)
+int launch_silu_mul(const void* gate, const void* up, void* out, size_t count, int dtype, bool pdl, cudaStream_t stream);
+
 // tcgen05 skinny-batch kernel, 1 <= M <= 64, N % 128 == 0 (w4a16_flat.cu)
 int launch_flat(const void* x, const void* qw, const void* sc, const void* sz, void* y, int M, int N, int K, int dtype,
                 bool pdl, const FlatTuning& tune, cudaStream_t stream);

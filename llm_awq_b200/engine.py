@@ -33,6 +33,10 @@ def lib() -> ctypes.CDLL:
         L.b200awq_w4a16_gemv_allreduce.restype = ci
         L.b200awq_w4a16_gemm_workspace_bytes.argtypes = [ci, ci, ci]
         L.b200awq_w4a16_gemm_workspace_bytes.restype = sz
+        L.b200awq_w4a16_mlp_front.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, vp, sz, vp]
+        L.b200awq_w4a16_mlp_front.restype = ci
+        L.b200awq_w4a16_mlp_front_workspace_bytes.argtypes = [ci, ci, ci]
+        L.b200awq_w4a16_mlp_front_workspace_bytes.restype = sz
         L.b200awq_rmsnorm.argtypes = [vp, vp, vp, ci, ci, ctypes.c_float, ci, vp]
         L.b200awq_rmsnorm.restype = ci
         L.b200awq_set_pdl.argtypes = [ci]

@@ -143,3 +143,109 @@ def test_rmsnorm_under_graph_replay_in_a_chain():
         assert torch.equal(c, want_c)
     n1 = LO.rmsnorm(np64(x0), np64(gamma), 1e-5, "f16")
     assert rel_err(np64(a), n1) < 1e-3
+
+
+# ------------------------------------------------------------------ fused gate + up + SiLU * mul
+def _mlp_front_abi(x, gate, up, M, N, K, dtype, ws=True):
+    y = torch.empty(M, N, dtype=dtype, device=DEV)
+    lib = P.lib()
+    nbytes = lib.b200awq_w4a16_mlp_front_workspace_bytes(M, N, K)
+    w = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=DEV) if ws else None
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    rc = lib.b200awq_w4a16_mlp_front(p(x), p(gate[0]), p(gate[1]), p(gate[2]), p(up[0]), p(up[1]), p(up[2]), p(y), M, N, K, 128,
+                                     0 if dtype == torch.float16 else 1, p(w) if ws else None, nbytes if ws else 0,
+                                     ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    return rc, y
+
+
+def _mlp_oracle(x, gate, up, dtype, rows=None):
+    tr = lambda t: (t[0].cpu().numpy(), np64(t[1]), np64(t[2]))
+    return LO.mlp_front(np64(x), tr(gate), tr(up), dtype=dt_name(dtype), rows=rows)
+
+
+@pytest.mark.parametrize("dtype", DTYPES, ids=["f16", "bf16"])
+@pytest.mark.parametrize("M", [1, 4, 7, 8, 64, 2048])
+@pytest.mark.parametrize("N,K", [(2816, 1024), (14336, 4096), (4608, 11008)])
+def test_mlp_front_vs_oracle(N, K, M, dtype):
+    """One fp16 token: the one-kernel path; everything else: two products + the elementwise kernel.  Against the oracle's
+    composition with the reference's roundings; the product of two rounded factors is within 2 ulp of T normwise."""
+    if M == 2048 and K == 11008:
+        pytest.skip("covered by the other shapes (keeps the oracle's float64 matmul short)")
+    gate, up = gen_layer(N, K, dtype, seed=N + 1, device=DEV), gen_layer(N, K, dtype, seed=N + 2, device=DEV)
+    x = (gen_x(M, K, dtype, seed=M + 5, device=DEV) * 0.5).contiguous()
+    rc, y = _mlp_front_abi(x, gate, up, M, N, K, dtype)
+    assert rc == 0, P.lib().b200awq_strerror(rc)
+    torch.cuda.synchronize()
+    rows = np.arange(0, N, 1 if M <= 8 and N < 4000 else 37)
+    want = _mlp_oracle(x, gate, up, dtype, rows=rows)
+    tol = 1.5e-3 if dtype == torch.float16 else 8e-3
+    assert rel_err(np64(y[:, rows]), want) < tol
+
+
+@pytest.mark.parametrize("split", [1, 2, 4])
+@pytest.mark.parametrize("N,K", [(40, 512), (600, 4096), (2376, 4224), (14336, 4096)])
+def test_mlp_front_one_token_kernel_equals_composition_bit_for_bit(N, K, split):
+    """The fused kernel sums each product in exactly the order the plain decode kernel does and applies the same
+    roundings: its output equals silu(gemv(gate)) * gemv(up) evaluated with torch on the plugin's GEMV results, up to
+    the last place of expf (a handful of elements may differ by one ulp)."""
+    dtype = torch.float16
+    os.environ["B200AWQ_DECODE_SPLIT"] = str(split)
+    P.lib().b200awq_reload_config()
+    try:
+        gate, up = gen_layer(N, K, dtype, seed=3, device=DEV), gen_layer(N, K, dtype, seed=4, device=DEV)
+        x = gen_x(1, K, dtype, seed=8, device=DEV)
+        rc, y = _mlp_front_abi(x, gate, up, 1, N, K, dtype, ws=False)     # the one-kernel path needs no workspace
+        assert rc == 0, P.lib().b200awq_strerror(rc)
+        eng = P.engine()
+        g = eng.gemv_forward_cuda_new(x, *gate, 1, N, K, 128)
+        u = eng.gemv_forward_cuda_new(x, *up, 1, N, K, 128)
+        want = torch.nn.functional.silu(g) * u
+        torch.cuda.synchronize()
+        ulp = _ulps(y, want, dtype)
+        assert int(ulp.max()) <= 1 and float((ulp > 0).float().mean()) < 5e-3
+        assert rel_err(np64(y), _mlp_oracle(x, gate, up, dtype)) < 1.5e-3
+    finally:
+        os.environ.pop("B200AWQ_DECODE_SPLIT")
+        P.lib().b200awq_reload_config()
+
+
+def test_mlp_front_plugin_and_module_mirror():
+    """awq_inference_engine.mlp_front_forward_cuda and llm_awq_b200.fused_mlp.QuantLlamaMLP (mirror of
+    tinychat/modules/fused_mlp.py:11-83): shapes [1, tokens, hidden], both token regimes, workspace handled by the shim."""
+    from llm_awq_b200.fused_mlp import QuantLlamaMLP
+    dtype, H, I = torch.float16, 1024, 2816
+
+    def wq(K, N, seed):
+        m = P.WQLinear(4, 128, K, N, False, DEV)
+        m.qweight, m.scales, m.scaled_zeros = gen_layer(N, K, dtype, seed=seed, device=DEV)
+        return m
+    gate, up, down = wq(H, I, 31), wq(H, I, 32), wq(I, H, 33)
+    mlp = QuantLlamaMLP(gate, down, up)
+    assert {"gate_proj_qweight", "gate_proj_scales", "gate_proj_scaled_zeros", "up_proj_qweight", "up_proj_scales",
+            "up_proj_scaled_zeros"} <= set(mlp.state_dict().keys())
+    for tokens in (1, 5, 40):
+        x = (gen_x(tokens, H, dtype, seed=tokens, device=DEV) * 0.5).view(1, tokens, H)
+        c = mlp.our_llama_mlp(x)
+        torch.cuda.synchronize()
+        assert c.shape == (1, tokens, I)
+        want = _mlp_oracle(x.view(tokens, H), (gate.qweight, gate.scales, gate.scaled_zeros),
+                           (up.qweight, up.scales, up.scaled_zeros), dtype)
+        assert rel_err(np64(c.view(tokens, I)), want) < 1.5e-3
+        y = mlp(x)
+        assert y.shape == (1, tokens, H) and torch.isfinite(y).all()
+    with pytest.raises(RuntimeError):
+        P.engine().mlp_front_forward_cuda(x.float(), gate.qweight, gate.scales, gate.scaled_zeros, up.qweight, up.scales,
+                                          up.scaled_zeros)
+
+
+def test_mlp_front_rejects_bad_arguments():
+    lib = P.lib()
+    a = torch.zeros(64, dtype=torch.float16, device=DEV)
+    p = ctypes.c_void_p(a.data_ptr())
+    args = lambda m, n, k, g, dt, ws, wsb: (p, p, p, p, p, p, p, p, m, n, k, g, dt, ws, wsb, None)
+    assert lib.b200awq_w4a16_mlp_front(*args(1, 4096, 4096, 64, 0, None, 0)) == -2      # group
+    assert lib.b200awq_w4a16_mlp_front(*args(1, 4096, 4096, 128, 5, None, 0)) == -4     # dtype
+    assert lib.b200awq_w4a16_mlp_front(*args(1, 4100, 4096, 128, 0, None, 0)) == -1     # n % 8
+    assert lib.b200awq_w4a16_mlp_front(*args(16, 4104, 4096, 128, 0, p, 1 << 30)) == -1  # n % 128 from 8 tokens
+    assert lib.b200awq_w4a16_mlp_front(*args(4, 4096, 4096, 128, 0, None, 0)) == -6     # workspace required beyond one token
+    assert lib.b200awq_w4a16_mlp_front_workspace_bytes(4, 4096, 4096) == 2 * 4 * 4096 * 2

@@ -117,6 +117,40 @@ size_t b200awq_w4a16_mlp_front_workspace_bytes(int m, int n, int k);
  * kernel).  m == 0 is a no-op. */
 int b200awq_rmsnorm(const void* x, const void* gamma, void* y, int m, int n, float eps, int dtype, void* stream);
 
+/* Decode-step attention over tinychat's KV-cache layout.  Replaces
+ *   single_query_attention(q, k, v, k_cache, v_cache, length_per_sample, alibi_slopes, timestep, rotary_embedding_dim,
+ *                          rotary_base, rotary_scale, neox_rotary_style)
+ *   reference: awq/kernels/csrc/attention/ft_attention.cpp:112-184, exported at csrc/pybind.cpp:24-27, called from
+ *              tinychat/modules/fused_attn.py:308-321.
+ * q [batch, heads, head_dim], k / v [batch, kv_heads, head_dim] with their own batch strides in ELEMENTS (they are
+ * usually views into the fused QKV output; the reference applies q's stride to all three, template.hpp:967-969), head
+ * stride head_dim, unit element stride; k_cache [batch, kv_heads, head_dim / 8,
+ * max_len, 8], v_cache [batch, kv_heads, max_len, head_dim], out [batch, heads, head_dim] contiguous.  The current
+ * step's q and k are rotated at position t = length_per_sample ? length_per_sample[b] : timestep (angle t * scale /
+ * base^(2i / rotary_dim); neox != 0 pairs (i, i + rotary_dim / 2), else (2i, 2i + 1)) and rounded to the element type;
+ * k and v are stored at cache slot t % max_len; out = softmax(q K^T / sqrt(head_dim)) V over the last min(t + 1,
+ * max_len) positions.  heads / kv_heads must be 1, 2, 4 or 8, head_dim a multiple of 8 up to 256 that divides 2048.
+ * `workspace`: >= b200awq_single_query_attention_workspace_bytes(...) bytes of device memory, ZERO before the first
+ * use, then owned by the kernels (they leave it zero where it matters); one workspace per stream.  ALiBi is not
+ * supported (the reference's alibi_slopes argument must be None). */
+int b200awq_single_query_attention(const void* q, const void* k, const void* v, void* k_cache, void* v_cache, void* out,
+                                   const int* length_per_sample, int batch, int heads, int kv_heads, int head_dim,
+                                   int max_len, int timestep, long long q_batch_stride, long long k_batch_stride,
+                                   long long v_batch_stride, int rotary_dim, float rotary_base,
+                                   float rotary_scale, int neox, int dtype, void* workspace, size_t workspace_bytes,
+                                   void* stream);
+size_t b200awq_single_query_attention_workspace_bytes(int batch, int heads, int kv_heads, int head_dim, int max_len);
+
+/* RoPE with explicit angles over a strided [s, b, h, d] tensor (prefill).  Replaces
+ *   fused_rope_with_pos_forward_func(input, freqs, transpose_output_memory)
+ *   reference: awq/kernels/csrc/rope_new/fused_rope_with_pos.cu:33-75,243-285, csrc/pybind.cpp:28, called from
+ *              tinychat/modules/fused_attn.py:253-254.
+ * y[s, b, h, i] = x[i] cos(f_i) + rot(x)[i] sin(f_i) for i < d2 with f_i = freqs[(b * S + s) * d2 + i] (fp32) and
+ * rot(x)[i] = -x[i + d2 / 2] for i < d2 / 2, x[i - d2 / 2] otherwise; elements i >= d2 are copied.  Strides in ELEMENTS
+ * for s, b, h, d of the input and of the output. */
+int b200awq_rope_with_pos(const void* x, const float* freqs, void* y, int s, int b, int h, int d, int d2,
+                          const long long in_strides[4], const long long out_strides[4], int dtype, void* stream);
+
 /* Names used by BASELINE.json's north_star; identical to the two launchers above. */
 int gemv_forward_4bit(const void* x, const void* qweight, const void* scales, const void* szeros,
                       void* y, int m, int n, int k, int group_size, int dtype, void* stream);

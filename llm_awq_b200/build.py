@@ -17,7 +17,7 @@ LIB = os.path.join(HERE, "lib", "libb200awq.so")
 EXT = os.path.join(HERE, "plugin", "awq_inference_engine" + sysconfig.get_config_var("EXT_SUFFIX"))
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
-KERNEL_SRCS = ("api.cu", "w4a16_decode.cu", "w4a16_ring.cu", "w4a16_stream.cu", "w4a16_umma.cu", "w4a16_flat.cu", "rmsnorm.cu", "silu_mul.cu")
+KERNEL_SRCS = ("api.cu", "w4a16_decode.cu", "w4a16_ring.cu", "w4a16_stream.cu", "w4a16_umma.cu", "w4a16_flat.cu", "rmsnorm.cu", "silu_mul.cu", "attention.cu")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC"]

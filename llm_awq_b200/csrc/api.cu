@@ -224,6 +224,39 @@ int b200awq_w4a16_mlp_front(const void* x, const void* gate_qweight, const void*
   return r;
 }
 
+size_t b200awq_single_query_attention_workspace_bytes(int batch, int heads, int kv_heads, int head_dim, int max_len) {
+  return b200awq::attention_workspace_bytes(batch, heads, kv_heads, head_dim, max_len);
+}
+
+int b200awq_single_query_attention(const void* q, const void* k, const void* v, void* k_cache, void* v_cache, void* out,
+                                   const int* length_per_sample, int batch, int heads, int kv_heads, int head_dim,
+                                   int max_len, int timestep, long long q_batch_stride, long long k_batch_stride,
+                                   long long v_batch_stride, int rotary_dim, float rotary_base,
+                                   float rotary_scale, int neox, int dtype, void* workspace, size_t workspace_bytes,
+                                   void* stream) {
+  if (dtype != B200AWQ_DTYPE_F16 && dtype != B200AWQ_DTYPE_BF16) return B200AWQ_ERR_DTYPE;
+  if (!q || !k || !v || !aligned16(k_cache) || !aligned16(v_cache) || !out) return B200AWQ_ERR_ALIGN;
+  if (int e = check_device()) return e;
+  const int r = b200awq::launch_single_query_attention(q, k, v, k_cache, v_cache, out, length_per_sample, batch, heads, kv_heads,
+                                                       head_dim, max_len, timestep, q_batch_stride, k_batch_stride, v_batch_stride, rotary_dim,
+                                                       rotary_base,
+                                                       rotary_scale, neox, dtype, workspace, workspace_bytes, pdl_enabled(),
+                                                       static_cast<cudaStream_t>(stream));
+  if (r == 0) g_launches.fetch_add(1, std::memory_order_relaxed);
+  return r;
+}
+
+int b200awq_rope_with_pos(const void* x, const float* freqs, void* y, int s, int b, int h, int d, int d2,
+                          const long long in_strides[4], const long long out_strides[4], int dtype, void* stream) {
+  if (dtype != B200AWQ_DTYPE_F16 && dtype != B200AWQ_DTYPE_BF16) return B200AWQ_ERR_DTYPE;
+  if (!x || !freqs || !y || !in_strides || !out_strides) return B200AWQ_ERR_ALIGN;
+  if (int e = check_device()) return e;
+  const int r = b200awq::launch_rope_with_pos(x, freqs, y, s, b, h, d, d2, in_strides, out_strides, dtype, pdl_enabled(),
+                                              static_cast<cudaStream_t>(stream));
+  if (r == 0) g_launches.fetch_add(1, std::memory_order_relaxed);
+  return r;
+}
+
 int b200awq_rmsnorm(const void* x, const void* gamma, void* y, int m, int n, float eps, int dtype, void* stream) {
   if (dtype != B200AWQ_DTYPE_F16 && dtype != B200AWQ_DTYPE_BF16) return B200AWQ_ERR_DTYPE;
   if (m < 0 || n < 1) return B200AWQ_ERR_SHAPE;

@@ -9,6 +9,7 @@
 #include <c10/cuda/CUDAGuard.h>
 #include <torch/extension.h>
 
+#include <map>
 #include <stdexcept>
 
 #include "../../include/b200awq.h"
@@ -146,11 +147,84 @@ void layernorm_forward_cuda(torch::Tensor _input, torch::Tensor _gamma, torch::T
         false);
 }
 
+// reference: awq/kernels/csrc/attention/ft_attention.cpp:112-184 (same checks, same argument order and defaults,
+// pybind.cpp:24-27).  alibi_slopes must be None; fp32 tensors are not dispatched.
+torch::Tensor single_query_attention(const torch::Tensor q, const torch::Tensor k, const torch::Tensor v, torch::Tensor k_cache,
+                                     torch::Tensor v_cache, c10::optional<const torch::Tensor> length_per_sample_,
+                                     c10::optional<const torch::Tensor> alibi_slopes_, const int timestep,
+                                     const int rotary_embedding_dim, const float rotary_base, const float rotary_scale,
+                                     const bool neox_rotary_style) {
+  TORCH_CHECK(q.is_cuda() && k.is_cuda() && v.is_cuda() && k_cache.is_cuda() && v_cache.is_cuda(), "tensors must be on CUDA");
+  const int batch_size = v_cache.size(0), nheads = q.size(1), nheads_kv = v_cache.size(1);
+  const int memory_max_seqlen = v_cache.size(2), headdim = v_cache.size(3);
+  TORCH_CHECK(q.sizes() == torch::IntArrayRef({batch_size, nheads, headdim}), "q must have shape (batch, nheads, headdim)");
+  TORCH_CHECK(k.sizes() == torch::IntArrayRef({batch_size, nheads_kv, headdim}), "k must have shape (batch, nheads_kv, headdim)");
+  TORCH_CHECK(v.sizes() == torch::IntArrayRef({batch_size, nheads_kv, headdim}), "v must have shape (batch, nheads_kv, headdim)");
+  TORCH_CHECK(k_cache.sizes() == torch::IntArrayRef({batch_size, nheads_kv, headdim / 8, memory_max_seqlen, 8}),
+              "k_cache must have shape (batch, nheads_kv, headdim / 8, max_seqlen, 8)");
+  TORCH_CHECK(q.stride(2) == 1 && q.stride(1) == headdim);
+  TORCH_CHECK(k.stride(2) == 1 && k.stride(1) == headdim);
+  TORCH_CHECK(v.stride(2) == 1 && v.stride(1) == headdim);
+  TORCH_CHECK(v_cache.is_contiguous() && k_cache.is_contiguous(), "caches must be contiguous");
+  const int dt = dtype_code(q, "single_query_attention");
+  TORCH_CHECK(k.scalar_type() == q.scalar_type() && v.scalar_type() == q.scalar_type() &&
+              k_cache.scalar_type() == q.scalar_type() && v_cache.scalar_type() == q.scalar_type());
+  TORCH_CHECK(!alibi_slopes_.has_value(), "b200awq: alibi_slopes is not supported by this build");
+  const int* lps = nullptr;
+  if (length_per_sample_.has_value()) {
+    const auto& l = length_per_sample_.value();
+    TORCH_CHECK(l.is_cuda() && l.is_contiguous() && l.dtype() == torch::kInt32 && l.numel() == batch_size);
+    lps = l.data_ptr<int>();
+  }
+  const c10::cuda::CUDAGuard guard(q.device());
+  torch::Tensor out = torch::empty({batch_size, nheads, headdim}, q.options());
+  // one zero-initialised workspace per (device, stream); the kernels leave it zero where it matters
+  static std::map<std::pair<int, void*>, torch::Tensor> workspaces;
+  const size_t need = b200awq_single_query_attention_workspace_bytes(batch_size, nheads, nheads_kv, headdim, memory_max_seqlen);
+  void* st = at::cuda::getCurrentCUDAStream().stream();
+  auto key = std::make_pair((int)q.get_device(), st);
+  auto it = workspaces.find(key);
+  if (it == workspaces.end() || (size_t)it->second.numel() < need) {
+    workspaces[key] = torch::zeros({(int64_t)need}, q.options().dtype(torch::kUInt8));
+    it = workspaces.find(key);
+  }
+  raise(b200awq_single_query_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(),
+                                       out.data_ptr(), lps, batch_size, nheads, nheads_kv, headdim, memory_max_seqlen, timestep,
+                                       (long long)q.stride(0), (long long)k.stride(0), (long long)v.stride(0), rotary_embedding_dim, rotary_base, rotary_scale,
+                                       neox_rotary_style ? 1 : 0, dt, it->second.data_ptr(), (size_t)it->second.numel(), st),
+        false);
+  return out;
+}
+
+// reference: awq/kernels/csrc/rope_new/fused_rope_with_pos.cu:243-285
+at::Tensor fused_rope_with_pos_forward_func(const at::Tensor& input, const at::Tensor& freqs, const bool transpose_output_memory) {
+  TORCH_CHECK(input.is_cuda() && freqs.is_cuda() && input.dim() == 4, "input must be a CUDA tensor [s, b, h, d]");
+  TORCH_CHECK(freqs.scalar_type() == at::ScalarType::Float && freqs.is_contiguous(), "freqs must be contiguous float32");
+  const int dt = dtype_code(input, "fused_rope_with_pos_forward_func");
+  const int s = input.size(0), b = input.size(1), h = input.size(2), d = input.size(3), d2 = freqs.size(-1);
+  TORCH_CHECK(freqs.numel() >= (int64_t)s * b * d2, "freqs must hold s * b * d2 angles");
+  auto opts = input.options().requires_grad(false);
+  at::Tensor output = transpose_output_memory ? torch::empty({b, s, h, d}, opts).transpose(0, 1) : torch::empty({s, b, h, d}, opts);
+  const long long is[4] = {input.stride(0), input.stride(1), input.stride(2), input.stride(3)};
+  const long long os[4] = {output.stride(0), output.stride(1), output.stride(2), output.stride(3)};
+  const c10::cuda::CUDAGuard guard(input.device());
+  raise(b200awq_rope_with_pos(input.data_ptr(), freqs.data_ptr<float>(), output.data_ptr(), s, b, h, d, d2, is, os, dt,
+                              at::cuda::getCurrentCUDAStream().stream()),
+        false);
+  return output;
+}
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "B200-native drop-in for llm-awq's awq_inference_engine (W4A16 path only)";
   m.def("gemm_forward_cuda_new", &gemm_forward_cuda_new, "New quantized GEMM kernel.");
   m.def("gemv_forward_cuda_new", &gemv_forward_cuda_new, "New quantized GEMV kernel.");
   m.def("layernorm_forward_cuda", &layernorm_forward_cuda, "FasterTransformer layernorm kernel");
+  m.def("single_query_attention", &single_query_attention, "Attention with a single query", py::arg("q"), py::arg("k"),
+        py::arg("v"), py::arg("k_cache"), py::arg("v_cache"), py::arg("length_per_sample_"), py::arg("alibi_slopes_"),
+        py::arg("timestep"), py::arg("rotary_embedding_dim") = 0, py::arg("rotary_base") = 10000.0f,
+        py::arg("rotary_scale") = 1.0f, py::arg("neox_rotary_style") = true);
+  m.def("fused_rope_with_pos_forward_func", &fused_rope_with_pos_forward_func,
+        "Fused rope forward function with B,S,D embedding");
   m.def("mlp_front_forward_cuda", &mlp_front_forward_cuda, "silu(x Wgate^T) * (x Wup^T) for W4A16 weights, one call");
   m.def("set_pdl", [](bool on) { return b200awq_set_pdl(on ? 1 : 0) != 0; }, "programmatic dependent launch on/off");
   m.def("launch_count", []() { return b200awq_launch_count(); }, "kernels launched by libb200awq so far");

@@ -88,6 +88,15 @@ int launch_decode_mlp_front(const void* x, const void* gqw, const void* gsc, con
 // out = silu(gate) * up over `count` elements, the reference's roundings (silu_mul.cu)
 int launch_silu_mul(const void* gate, const void* up, void* out, size_t count, int dtype, bool pdl, cudaStream_t stream);
 
+// single-query (decode-step) attention over tinychat's KV-cache layout + RoPE over [s, b, h, d] (attention.cu)
+size_t attention_workspace_bytes(int batch, int heads, int kv_heads, int head_dim, int max_len);
+int launch_single_query_attention(const void* q, const void* k, const void* v, void* k_cache, void* v_cache, void* out,
+                                  const int* length_per_sample, int batch, int heads, int kv_heads, int head_dim, int max_len,
+                                  int timestep, long long q_batch_stride, long long k_batch_stride, long long v_batch_stride, int rotary_dim, float rotary_base, float rotary_scale,
+                                  int neox, int dtype, void* workspace, size_t workspace_bytes, bool pdl, cudaStream_t stream);
+int launch_rope_with_pos(const void* x, const float* freqs, void* y, int s, int b, int h, int d, int d2, const long long* in_strides,
+                         const long long* out_strides, int dtype, bool pdl, cudaStream_t stream);
+
 // tcgen05 skinny-batch kernel, 1 <= M <= 64, N % 128 == 0 (w4a16_flat.cu)
 int launch_flat(const void* x, const void* qw, const void* sc, const void* sz, void* y, int M, int N, int K, int dtype,
                 bool pdl, const FlatTuning& tune, cudaStream_t stream);

@@ -37,6 +37,14 @@ def lib() -> ctypes.CDLL:
         L.b200awq_w4a16_mlp_front.restype = ci
         L.b200awq_w4a16_mlp_front_workspace_bytes.argtypes = [ci, ci, ci]
         L.b200awq_w4a16_mlp_front_workspace_bytes.restype = sz
+        ll, fl = ctypes.c_longlong, ctypes.c_float
+        L.b200awq_single_query_attention.argtypes = [vp, vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, ll, ll, ll, ci, fl, fl, ci, ci,
+                                                     vp, sz, vp]
+        L.b200awq_single_query_attention.restype = ci
+        L.b200awq_single_query_attention_workspace_bytes.argtypes = [ci, ci, ci, ci, ci]
+        L.b200awq_single_query_attention_workspace_bytes.restype = sz
+        L.b200awq_rope_with_pos.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, vp, vp, ci, vp]
+        L.b200awq_rope_with_pos.restype = ci
         L.b200awq_rmsnorm.argtypes = [vp, vp, vp, ci, ci, ctypes.c_float, ci, vp]
         L.b200awq_rmsnorm.restype = ci
         L.b200awq_set_pdl.argtypes = [ci]

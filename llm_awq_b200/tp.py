@@ -102,10 +102,35 @@ class RowParallelWQLinear(nn.Module):
         self.group = group
         self.world = world
 
+    # Prefill: the [tokens, out_features] partial is tens of MB (33.5 MB at 2048 x 8192 fp16) and its all-reduce is
+    # bandwidth-bound, so the row-parallel GEMM is chunked along the TOKEN dimension and the all-reduce of chunk i is
+    # issued asynchronously (NCCL runs it on the process group's own stream over NVLink) while the tensor-core kernel of
+    # chunk i + 1 runs on the compute stream.  Chunks are row ranges of ONE output tensor, so the result
+    # is the same tensor the unchunked path produces; every rank issues the same chunk sequence.
+    overlap_min_tokens = 512     # below this the all-reduce is latency-bound and one call is better
+    overlap_chunks = 4
+
     def forward(self, x_local):
+        m = x_local.numel() // x_local.shape[-1]
+        if self.world > 1 and m >= self.overlap_min_tokens and self.overlap_chunks > 1:
+            return self._forward_overlapped(x_local, m)
         y = self.local(x_local)
         if self.world > 1:
             torch.distributed.all_reduce(y, op=torch.distributed.ReduceOp.SUM, group=self.group)
+        return y + self.bias if self.bias is not None else y
+
+    def _forward_overlapped(self, x_local, m):
+        x2 = x_local.reshape(m, x_local.shape[-1])
+        step = -(-m // self.overlap_chunks)
+        step = -(-step // 128) * 128                      # whole 128-token tiles of the tensor-core kernel
+        parts, works = [], []
+        for lo in range(0, m, step):
+            yc = self.local(x2[lo:lo + step])            # compute stream
+            works.append(torch.distributed.all_reduce(yc, op=torch.distributed.ReduceOp.SUM, group=self.group, async_op=True))
+            parts.append(yc)
+        for w in works:
+            w.wait()                                      # the compute stream waits for the collective's stream
+        y = torch.cat(parts, dim=0).reshape(*x_local.shape[:-1], parts[0].shape[-1])
         return y + self.bias if self.bias is not None else y
 
 

@@ -53,3 +53,78 @@ def mlp_front(x, gate, up, dtype: str = "f16", rows=None) -> np.ndarray:
     g = rn(O.wq_linear_forward(x, *gate, dtype=dtype, rows=rows))
     u = rn(O.wq_linear_forward(x, *up, dtype=dtype, rows=rows))
     return rn(rn(silu(g)) * u)
+
+
+# ------------------------------------------------------------------------------------------------- attention + RoPE
+def rope_pair_angles(n_pairs: int, rot_dim: int, t: float, base: float, scale: float) -> np.ndarray:
+    """``rotary_embedding_coefficient`` (awq/kernels/csrc/attention/decoder_masked_multihead_attention_utils.h:
+    1282-1287): angle of pair ``i`` at step ``t`` = ``(t * scale) / base ** (2 i / rot_dim)``."""
+    i = np.arange(n_pairs, dtype=np.float64)
+    return (t * scale) / np.power(float(base), 2.0 * i / rot_dim)
+
+
+def rope_rotate(x: np.ndarray, t: float, rot_dim: int, base: float, scale: float, neox: bool, dtype: str) -> np.ndarray:
+    """Rotate the last dimension of ``x`` ([..., D]) at position ``t`` and round to ``dtype``
+    (decoder_masked_multihead_attention_template.hpp:1080-1135 with utils.h:1290-1296: x' = c x - s y, y' = c y + s x;
+    neox style pairs (i, i + rot_dim / 2), :1088-1135, else (2 i, 2 i + 1), :1080-1087; the vectors are of T)."""
+    x = np.array(x, dtype=np.float64)
+    out = x.copy()
+    half = rot_dim // 2
+    ang = rope_pair_angles(half, rot_dim, t, base, scale)
+    c, s = np.cos(ang), np.sin(ang)
+    if neox:
+        a, b = x[..., :half], x[..., half:rot_dim]
+        out[..., :half], out[..., half:rot_dim] = c * a - s * b, c * b + s * a
+    else:
+        a, b = x[..., 0:rot_dim:2], x[..., 1:rot_dim:2]
+        out[..., 0:rot_dim:2], out[..., 1:rot_dim:2] = c * a - s * b, c * b + s * a
+    return O.rounder(dtype)(out)
+
+
+def single_query_attention(q, k, v, k_cache, v_cache, timestep, rot_dim, base=10000.0, scale=1.0, neox=True, dtype="f16",
+                           length_per_sample=None):
+    """``single_query_attention`` (awq/kernels/csrc/attention/ft_attention.cpp:112-184 ->
+    decoder_masked_multihead_attention_template.hpp).  q [B, H, D], k / v [B, Hkv, D]; k_cache [B, Hkv, D / 8, L, 8] and
+    v_cache [B, Hkv, L, D] are UPDATED IN PLACE (float64 arrays holding T values) at slot t % L (:1148-1175, :1424-1440);
+    returns out [B, H, D] rounded to T.  tlength per sample = length_per_sample[b] or timestep (:975-978); positions
+    attended to: max(0, t + 1 - L) .. t (:979); logits = q . k / sqrt(D) (:1200, :1323), softmax and the sum over
+    positions in float64 (the reference: fp32, logits rounded to T before the product with V -- accumulation-level
+    differences, covered by the tests' tolerance)."""
+    q, k, v = (np.asarray(t, dtype=np.float64) for t in (q, k, v))
+    B, H, D = q.shape
+    Hkv, L = v_cache.shape[1], v_cache.shape[2]
+    G = H // Hkv
+    rn = O.rounder(dtype)
+    out = np.zeros((B, H, D))
+    for b in range(B):
+        t = int(length_per_sample[b]) if length_per_sample is not None else int(timestep)
+        qr = rope_rotate(q[b], t, rot_dim, base, scale, neox, dtype) if rot_dim > 0 else q[b]
+        kr = rope_rotate(k[b], t, rot_dim, base, scale, neox, dtype) if rot_dim > 0 else k[b]
+        slot = t % L
+        k_cache[b, :, :, slot, :] = kr.reshape(Hkv, D // 8, 8)
+        v_cache[b, :, slot, :] = v[b]
+        first = max(0, t + 1 - L)
+        slots = [p % L for p in range(first, t + 1)]
+        for h in range(H):
+            kv = h // G
+            K = k_cache[b, kv][:, slots, :].transpose(1, 0, 2).reshape(len(slots), D)
+            V = v_cache[b, kv][slots]
+            s = (K @ qr[h]) / np.sqrt(D)
+            p = np.exp(s - s.max())
+            out[b, h] = (p / p.sum()) @ V
+    return rn(out)
+
+
+def rope_with_pos(x: np.ndarray, freqs: np.ndarray, dtype: str = "f16") -> np.ndarray:
+    """``fused_rope_with_pos_forward_func`` (awq/kernels/csrc/rope_new/fused_rope_with_pos.cu:33-75): x [s, b, h, d],
+    angle of (s_id, b_id, i) = freqs.flat[(b_id * S + s_id) * d2 + i] (:46); y = x cos + rot(x) sin for i < d2 with
+    rot(x)[i] = -x[i + d2/2] (i < d2/2) else x[i - d2/2] (:51-56); the rest copied (:60-72); fp32 math, one rounding."""
+    x = np.asarray(x, dtype=np.float64)
+    S, B, Hh, D = x.shape
+    d2 = freqs.shape[-1]
+    f = np.asarray(freqs, dtype=np.float64).reshape(-1)[: B * S * d2].reshape(B, S, d2).transpose(1, 0, 2)[:, :, None, :]
+    y = x.copy()
+    xr = x[..., :d2]
+    rot = np.concatenate([-xr[..., d2 // 2:], xr[..., : d2 // 2]], axis=-1)
+    y[..., :d2] = xr * np.cos(f) + rot * np.sin(f)
+    return O.rounder(dtype)(y)

@@ -42,6 +42,35 @@ def _import_reference():
     return qmodule, ns["pseudo_quantize_tensor"]
 
 
+def _import_repacker():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_repacker", os.path.join(REF, "tinychat/offline-weight-repacker.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def repacker_golden():
+    """tests/golden/reference_repacker.npz: v1 tensors and what the reference's offline repacker makes of them
+    (tinychat/offline-weight-repacker.py:8-79), for llm_awq_b200/repack.py."""
+    rp = _import_repacker()
+    g = torch.Generator().manual_seed(77)
+    out = {}
+    for idx, (N, K, G) in enumerate([(8, 128, 128), (16, 256, 128), (64, 1024, 128), (32, 2048, 128)]):
+        qw = torch.randint(-2 ** 31, 2 ** 31 - 1, (N, K // 8), generator=g, dtype=torch.int64).to(torch.int32)
+        ng = K // G
+        scales = (0.004 + 0.012 * torch.rand(N, ng, generator=g)).half()
+        qz = torch.randint(-2 ** 31, 2 ** 31 - 1, (N, -(-ng // 8)), generator=g, dtype=torch.int64).to(torch.int32)
+        out[f"r{idx}_qweight_v1"] = qw.numpy()
+        out[f"r{idx}_scales_v1"] = scales.float().numpy()
+        out[f"r{idx}_qzeros_v1"] = qz.numpy()
+        out[f"r{idx}_unpacked"] = rp.qweight_unpack(qw).numpy().astype(np.uint8)
+        out[f"r{idx}_qweight_v2"] = rp.qweight_pack_v1_to_v2(qw, 4, 64).numpy()
+        out[f"r{idx}_scaled_zeros"] = rp.multiply_scale_qzero_negative(scales, qz, zp_shift=-8).float().numpy()
+    np.savez_compressed(os.path.join(HERE, "reference_repacker.npz"), **out)
+    print("wrote reference_repacker.npz", len(out), "arrays")
+
+
 def main():
     qmodule, pseudo_quantize_tensor = _import_reference()
     g = torch.Generator().manual_seed(20260922)
@@ -120,3 +149,4 @@ def main():
 
 if __name__ == "__main__":
     main()
+    repacker_golden()

@@ -103,6 +103,14 @@ def _worker(rank, world, port, out_dir):
     h = col(x)                                   # [3, inter / world], no communication
     y = row(h.to(torch.float16).float())         # local product + ONE all-reduce + bias
     torch.save(y, os.path.join(out_dir, f"y{rank}.pt"))
+    # prefill-sized token count: the chunked compute / all-reduce overlap path gives the same tensor as one all-reduce
+    xb = gen_x(700, hidden, seed=5).float()
+    hb = col(xb).to(torch.float16).float()
+    row.overlap_min_tokens, row.overlap_chunks = 512, 4
+    y_over = row(hb)
+    row.overlap_chunks = 1
+    y_one = row(hb)
+    assert y_over.shape == y_one.shape == (700, hidden) and torch.equal(y_over, y_one)
     dist.barrier()
     dist.destroy_process_group()
 

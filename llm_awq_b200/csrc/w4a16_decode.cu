@@ -629,9 +629,9 @@ int launch_decode_impl(const void* x, const void* qw, const void* sc, const void
   int off = 0;
   L.bars = off, off += 8 * (2 * kDecMaxSlots + 2 * kDecRed + kDecMaxRb);
   off = (off + 127) & ~127;
+  const int cons = tune.warps == 8 ? 8 : 16;
   L.x = off, off += ngr * kDecGroupBytes;
   L.gx = off, off += ngr * 4 * 8;
-  const int cons = tune.warps == 8 ? 8 : 16;
   L.red = off, off += kDecRed * cons * 16 * nt * 4;
   L.xchg = off, off += S * nrb_max * 16 * nt * 4;  // the peers' sums (S - 1 regions) + rank 0's own parked sums
   off = (off + 127) & ~127;

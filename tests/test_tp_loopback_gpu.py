@@ -7,7 +7,8 @@ widths sharing one exchange are all exercised on the 1-GPU test box (VERDICT r1,
 CUDA-graph replay, is tests/test_tp_gpu.py -- a graph's branches are not GUARANTEED to run concurrently on one device,
 and ranks that wait for each other must be).
 
-All ranks' CTAs must be co-resident (they wait for each other): shapes here are small (<= 64 CTAs per rank)."""
+All ranks' CTAs must be co-resident (they wait for each other).  The streaming kernel's grids here are small (<= 64 CTAs
+per rank)."""
 import ctypes
 
 import numpy as np

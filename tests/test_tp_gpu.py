@@ -61,7 +61,7 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.multigpu
 def test_column_then_row_parallel_on_kernels_nccl(tmp_path):
     from oracle import w4a16_oracle as O
     from awq_testutil import gen_layer, gen_x, np64, rel_err

@@ -71,8 +71,8 @@ __device__ __forceinline__ unsigned long long dec_globaltimer_ns() {
 #define DEC_DRY 0
 #endif
 
-// consumer warps per CTA: 8 (two groups per batch, <= 102 registers) or 16 (one group per batch, <= 56 registers); warp w
-// owns the groups g % CONS == w of every piece.  + producer warp + finisher warp.
+// consumer warps per CTA: 16 (default, <= 56 registers) or 8 (<= 102 registers); warp w owns the groups g % CONS == w of every
+// piece.  + producer warp + finisher warp.
 constexpr int kDecPiece = 32;                          // groups of 128 input channels per bulk copy (8 KB of one quad row)
 constexpr int kDecQuadBytes = kDecPiece * 256;         // 4 channels x 4096 k, packed
 constexpr int kDecQuadB = kDecQuadBytes + 16;          // offset of a slot's second quad row (bank skew)
@@ -156,7 +156,6 @@ __global__ void __launch_bounds__((CONS + 2) * 32, 2) w4a16_decode_kernel(const 
   constexpr int kDecCons = CONS;
   constexpr int NT = FUSED ? 2 : 1;   // weight sets
   constexpr int RW = 16 * NT;         // partial sums per row block and warp
-  constexpr int kBatch = CONS == 8 ? 2 : 1;  // groups whose loads are issued together
   extern __shared__ __align__(128) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   DEC_STAMP(0);
@@ -370,7 +369,7 @@ __global__ void __launch_bounds__((CONS + 2) * 32, 2) w4a16_decode_kernel(const 
   // so no CTA-wide barrier stands between the dependency wait and the first MAC.
   const int c = lane >> 2, tig = lane & 3;
   const uint32_t xd_u32 = smem_u32(smem + L.x);
-  float2* gx = reinterpret_cast<float2*>(smem + L.gx);  // [group][tig] {e_g 2^-7 tig / 16 (0 for tig 3), X_g for tig 0 else 0}
+  float* gx = reinterpret_cast<float*>(smem + L.gx);  // [group][tig]: e_g 2^-7 tig / 16 for the digit lanes tig < 3, X_g = sum_k x_k for tig 3
   {
     // Digits.  A digit word [column 2 d + par][u][m] (par 0: low-nibble channels, 1: high-nibble channels) holds the
     // four input channels m * 32 + par * 8 + {0, 16} + 2 u + {0, 1} of the group (see the packed layout in
@@ -440,7 +439,7 @@ __global__ void __launch_bounds__((CONS + 2) * 32, 2) w4a16_decode_kernel(const 
             const float X = e * fmaf((float)s2, 6.103515625e-05f, fmaf((float)s1, 0.0078125f, (float)s0));
             // the consumers form 16 * (low-nibble sum) + (high-nibble sum): the 1 / 16 lives here
             const float sc16 = lane == 0 ? 0.0625f : (lane == 1 ? 0.0625f * 0.0078125f : 0.0625f * 6.103515625e-05f);
-            gx[Gl * 4 + lane] = make_float2(lane == 3 ? 0.f : e * sc16, lane == 0 ? X : 0.f);
+            gx[Gl * 4 + lane] = lane == 3 ? X : e * sc16;
           }
         }
       }
@@ -459,7 +458,10 @@ __global__ void __launch_bounds__((CONS + 2) * 32, 2) w4a16_decode_kernel(const 
   const uint32_t sc_off = (uint32_t)(kDecScaleOff + (c >> 2) * (2 * kDecPiece * 8) + (c & 3) * 2);  // + group * 8; zeros + 256
   const uint32_t ring_u32 = smem_u32(ring);
   const uint32_t xd_lane = xd_u32 + (uint32_t)(c * 64 + tig * 16);  // columns 6, 7 read the neighbouring words: ignored
-  const uint32_t gx_lane = smem_u32(gx) + (uint32_t)tig * 8u;
+  const uint32_t gx_lane = smem_u32(gx) + (uint32_t)tig * 4u;
+  // the lanes tig < 3 carry one digit each and apply the SCALE; the lanes tig == 3 (whose MMA columns carry no digit) apply
+  // the ZERO term z_g X_g: one 16-bit load, one conversion and one FMA per octet for every lane
+  const uint32_t coef_sel = tig == 3 ? (uint32_t)(kDecPiece * 8) : 0u;  // zeros sit 256 B after the scales
   const int zero4[4] = {0, 0, 0, 0};
 
   int slot = 0, use = 0;
@@ -483,43 +485,36 @@ __global__ void __launch_bounds__((CONS + 2) * 32, 2) w4a16_decode_kernel(const 
       const uint32_t sb_u32 = ring_u32 + (uint32_t)slotB * kDecSlotBytes;  // == sa_u32 without a second octet
       const uint32_t w_lane = (ldsm_b ? sb_u32 : sa_u32) + ldsm_off;
       if (!DEC_DRY) {
-        // kBatch groups per batch, every shared-memory load of the batch issued before the first MAC; with 8 warps two
-        // groups per warp and two warps per scheduler are in flight, with 16 warps one group and four warps.
-        for (int g0 = warp; g0 < ng; g0 += kBatch * kDecCons) {
-          const bool on1 = kBatch > 1 && g0 + kDecCons < ng;  // warp-uniform
-          uint32_t wq[kBatch][2][4];
-          uint4 bv[kBatch];
-          float2 gxv[kBatch];
-          uint16_t sA[kBatch], zA[kBatch], sB[kBatch], zB[kBatch];
-#pragma unroll
-          for (int j = 0; j < kBatch; ++j) {
-            const int gi = (j == 0 || on1) ? g0 + j * kDecCons : g0;
-            const int Gl = p * kDecPiece + gi;
-            dec_ldsm4(wq[j][0], w_lane + (uint32_t)gi * 256u);
-            dec_ldsm4(wq[j][1], w_lane + (uint32_t)gi * 256u + 128u);
-            bv[j] = dec_lds128(xd_lane + (uint32_t)Gl * kDecGroupBytes);
-            asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(gxv[j].x), "=f"(gxv[j].y) : "r"(gx_lane + (uint32_t)Gl * 32u));
-            const uint32_t sp = sa_u32 + sc_off + (uint32_t)gi * 8u, sq = sb_u32 + sc_off + (uint32_t)gi * 8u;
-            sA[j] = dec_lds16(sp), zA[j] = dec_lds16(sp + kDecPiece * 8);
-            sB[j] = dec_lds16(sq), zB[j] = dec_lds16(sq + kDecPiece * 8);  // == the first octet's without a second one
-          }
-#pragma unroll
-          for (int j = 0; j < kBatch; ++j) {
-            if (j == 1 && !on1) break;
-            int accR[4], accH[4];
-            dec_imma(accR, wq[j][0][0], wq[j][0][1], wq[j][0][2], wq[j][0][3], bv[j].x, bv[j].y, zero4);
-            dec_imma(accH, wq[j][0][0] & 0xf0f0f0f0u, wq[j][0][1] & 0xf0f0f0f0u, wq[j][0][2] & 0xf0f0f0f0u,
-                     wq[j][0][3] & 0xf0f0f0f0u, bv[j].x, bv[j].y, zero4);
-            dec_imma(accR, wq[j][1][0], wq[j][1][1], wq[j][1][2], wq[j][1][3], bv[j].z, bv[j].w, accR);
-            dec_imma(accH, wq[j][1][0] & 0xf0f0f0f0u, wq[j][1][1] & 0xf0f0f0f0u, wq[j][1][2] & 0xf0f0f0f0u,
-                     wq[j][1][3] & 0xf0f0f0f0u, bv[j].z, bv[j].w, accH);
-            // this lane's columns 2 tig, 2 tig + 1 = digit tig: low-nibble sum accR[0] - accH[0], high-nibble sum
-            // accH[1] / 16 -> T16 = 16 (accR[0] - accH[0]) + accH[1], the 1 / 16 is folded into gxv.x
-            const float t0f = (float)(((accR[0] - accH[0]) << 4) + accH[1]);
-            const float t1f = (float)(((accR[2] - accH[2]) << 4) + accH[3]);
-            y0 = fmaf(bits16_to_float(zA[j], kBf16), gxv[j].y, fmaf(bits16_to_float(sA[j], kBf16) * gxv[j].x, t0f, y0));
-            y1 = fmaf(bits16_to_float(zB[j], kBf16), gxv[j].y, fmaf(bits16_to_float(sB[j], kBf16) * gxv[j].x, t1f, y1));
-          }
+        // per-item bases; a group adds its index times a constant (folded into the instructions for the two groups of
+        // a full piece)
+        const uint32_t xd_item = xd_lane + (uint32_t)(p * kDecPiece) * kDecGroupBytes;
+        const uint32_t gx_item = gx_lane + (uint32_t)(p * kDecPiece) * 16u;
+        const uint32_t cA_item = sa_u32 + sc_off + coef_sel, cB_item = sb_u32 + sc_off + coef_sel;
+        auto mac_group = [&](const uint32_t gi) {
+          uint32_t w0[4], w1[4];
+          dec_ldsm4(w0, w_lane + gi * 256u);
+          dec_ldsm4(w1, w_lane + gi * 256u + 128u);
+          const uint4 bv = dec_lds128(xd_item + gi * (uint32_t)kDecGroupBytes);
+          float gv;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(gv) : "r"(gx_item + gi * 16u));
+          const uint16_t cA = dec_lds16(cA_item + gi * 8u), cB = dec_lds16(cB_item + gi * 8u);
+          int accR[4], accH[4];
+          dec_imma(accR, w0[0], w0[1], w0[2], w0[3], bv.x, bv.y, zero4);
+          dec_imma(accH, w0[0] & 0xf0f0f0f0u, w0[1] & 0xf0f0f0f0u, w0[2] & 0xf0f0f0f0u, w0[3] & 0xf0f0f0f0u, bv.x, bv.y, zero4);
+          dec_imma(accR, w1[0], w1[1], w1[2], w1[3], bv.z, bv.w, accR);
+          dec_imma(accH, w1[0] & 0xf0f0f0f0u, w1[1] & 0xf0f0f0f0u, w1[2] & 0xf0f0f0f0u, w1[3] & 0xf0f0f0f0u, bv.z, bv.w, accH);
+          // digit lanes: columns 2 tig, 2 tig + 1 = digit tig: low-nibble sum accR[0] - accH[0], high-nibble sum accH[1] / 16
+          // -> T16 = 16 (accR[0] - accH[0]) + accH[1] (the 1 / 16 is folded into gv); zero-term lanes: T = 1, gv = X_g
+          const float t0f = tig == 3 ? 1.f : (float)(((accR[0] - accH[0]) << 4) + accH[1]);
+          const float t1f = tig == 3 ? 1.f : (float)(((accR[2] - accH[2]) << 4) + accH[3]);
+          y0 = fmaf(bits16_to_float(cA, kBf16) * gv, t0f, y0);
+          y1 = fmaf(bits16_to_float(cB, kBf16) * gv, t1f, y1);  // second octet absent: a copy of the first, never stored
+        };
+        if (ng == kDecPiece && kDecCons == 16) {
+          mac_group((uint32_t)warp);
+          mac_group((uint32_t)warp + 16u);
+        } else {
+          for (int gi = warp; gi < ng; gi += kDecCons) mac_group((uint32_t)gi);
         }
       }
       DEC_CLK(t2);
@@ -631,7 +626,7 @@ int launch_decode_impl(const void* x, const void* qw, const void* sc, const void
   off = (off + 127) & ~127;
   const int cons = tune.warps == 8 ? 8 : 16;
   L.x = off, off += ngr * kDecGroupBytes;
-  L.gx = off, off += ngr * 4 * 8;
+  L.gx = off, off += ngr * 4 * 4;
   L.red = off, off += kDecRed * cons * 16 * nt * 4;
   L.xchg = off, off += S * nrb_max * 16 * nt * 4;  // the peers' sums (S - 1 regions) + rank 0's own parked sums
   off = (off + 127) & ~127;

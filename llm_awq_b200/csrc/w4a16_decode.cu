@@ -22,7 +22,7 @@
 // cp.async per group and quad row), one `full` mbarrier.  The second quad row sits 8 KB + 16 B after the first: the
 // eight 16-byte rows of every ldmatrix phase then hit eight different bank groups.
 //
-// Arithmetic (exact int32 partial sums, fp32 scale application; w4a16_ring.cu introduced it as "MODE 8"):
+// Arithmetic (exact int32 partial sums, fp32 scale application):
 //   a packed byte b = 16 h + l holds two weights of one channel.  With the activation vector split, per 128-k group,
 //   into three signed 7-bit digits of a block-fixed-point number  x_k = e_g (d0 + d1 / 128 + d2 / 16384)  (e_g a power
 //   of two, |d| <= 64: every fp16 / bf16 activation is represented to 2^-21 of the group's largest magnitude),

@@ -59,7 +59,7 @@ int launch_umma(const void* x, const void* qw, const void* sc, const void* sz, v
                 bool pdl, const UmmaTuning& tune, cudaStream_t stream);
 
 struct RingTuning {
-  int mode = -1;   // -1 = auto (fp16: 8 for one token else 2, bf16: 0); 0, 2 or 8      [env B200AWQ_RING_MODE]
+  int mode = -1;   // -1 = auto (fp16: 2, bf16: 0); 0 or 2                               [env B200AWQ_RING_MODE]
   int split = 0;   // 0 = auto, 1 = no k split, 2 = k split over a 2-CTA cluster      [env B200AWQ_RING_SPLIT]
   int slots = 0;   // 0 = as many ring slots as fit next to a second CTA, else a cap  [env B200AWQ_RING_SLOTS]
 };

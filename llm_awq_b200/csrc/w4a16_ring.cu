@@ -1,4 +1,6 @@
-// Persistent, warp-specialised W4A16 decode kernel (GEMV, 1 <= M <= 8 tokens): the HBM-bound hot path.
+// Persistent, warp-specialised W4A16 decode kernel for SEVERAL tokens (2 <= M <= 4 by dispatch, up to 8) and for bf16:
+// fp16 / bf16 tensor-core MACs with the tokens in the MMA columns.  (One fp16 token is served by w4a16_decode.cu, the
+// third generation of this structure: 8 KB copies instead of the 4 KB ones below, int8-digit MACs.)
 //
 // Replaces the reference's gemv_kernel (quantization_new/gemv/gemv_cuda.cu:74-229).  B200-first design, sized
 // from the round-1 measurements (profiles/README.md, "What limits decode"):
@@ -456,353 +458,6 @@ __global__ void __launch_bounds__(kRingThreads, 2) w4a16_ring_kernel(const __gri
 }
 
 
-// =====================================================================================================================
-// MODE 8: one token, activations as exact int8 digits, packed bytes straight into u8 x s8 tensor-core MACs.
-//
-// Measured on B200 (scripts/probes/mma_probe.cu, profiles/r2_mma_probe.txt): IMMA.16832.U8.S8 issues at the same 8
-// cycles per instruction per scheduler as HMMA.16816 (twice the MACs), LOP3 / PRMT are half rate (2 cycles).  The fp16
-// path above spends 40 half-rate ALU ops + 8 HMMA per 128-k group of 16 channels and is latency / ALU bound at ~20 B
-// of packed weights per clock per SM.  Here a packed byte b = 16 h + l (two weights, high and low nibble) is fed to the
-// tensor core AS IS:
-//     raw  = sum_k b_k * LO_k                       (LO_k: activation digit of the LOW nibble's input channel)
-//     high = sum_k (b_k & 0xf0) * [LO_k | HI_k]     (one LOP3 per packed word; HI_k: digit of the HIGH nibble's channel)
-//     sum_k l_k x_lo + h_k x_hi  =  raw - high.LO + high.HI / 16            -- exact in int32
-// so a group costs 8 LOP3 + 4 IMMA.  The activation vector is split, per 128-k group, into three signed 7-bit digits
-// of a block-fixed-point number  x_k = e_g (d0 + d1 / 128 + d2 / 16384), e_g a power of two, |d| <= 64: exact for
-// every fp16 / bf16 value within 2^-10 of the group's largest magnitude and to 2^-21 of that magnitude otherwise
-// (fp16 has an 11-bit significand); the digits occupy the 8 "token" columns of the MMA (column 2 d: LO digits, column
-// 2 d + 1: HI digits), which a single token leaves free.  y += s (e_g sum_d 2^-7d T_d) + z X_g with X_g = sum x_k in
-// fp32: no bias term and no cancellation (the fp16 MODE 2 subtracts 1024 X).  16 consumer warps (one group of a slot
-// each) fit at <= 56 registers next to a second CTA.
-constexpr int kR8Cons = 16;
-constexpr int kR8Threads = (kR8Cons + 2) * 32;  // + producer warp + finisher warp
-constexpr int kR8GroupBytes = 6 * 4 * 16;       // digits of one group: [column 0..5][tig][32-k block m] words
-constexpr int kR8Red = 4;                       // row blocks whose 16 x 16 partial sums may wait for the finisher
-
-__device__ __forceinline__ void imma_16832(int (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
-                                           uint32_t b1, const int (&c)[4]) {
-  asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
-      : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])
-      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]));
-}
-__device__ __forceinline__ void sts8(uint32_t addr, int v) {
-  asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
-
-template <typename T>
-__global__ void __launch_bounds__(kR8Threads, 2) w4a16_ring8_kernel(const __grid_constant__ RingArgs a) {
-  constexpr bool kBf16 = TypeTraits<T>::kIsBf16;
-  extern __shared__ __align__(128) uint8_t smem[];
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  RING_STAMP(0);
-  const RingLayout& L = a.L;
-  const int S = a.S, NS = a.NS, N = a.N, K = a.K;
-  const int rank = (S > 1) ? (int)cluster_ctarank() : 0;
-  const int unit = (S > 1) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int O = N >> 3, G = K >> 7;
-  const int o_lo = (int)(((long long)unit * O) / a.units), o_hi = (int)(((long long)(unit + 1) * O) / a.units);
-  const int nrb = (o_hi - o_lo + 1) >> 1;
-  const int kg_lo = (rank * G) / S, kg_hi = ((rank + 1) * G) / S;
-  const int ngr = kg_hi - kg_lo;
-  const int nsl = (ngr + kSlotGroups - 1) / kSlotGroups;
-  const int items = nrb * nsl;
-
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + NS;
-  uint64_t* rbfull = bars + 2 * NS;
-  uint64_t* rbfree = rbfull + kR8Red;
-  uint64_t* xch = rbfree + kR8Red;
-  uint8_t* ring = smem + L.ring;
-  float* red = reinterpret_cast<float*>(smem + L.red);    // [kR8Red][warp][16 ch]
-  float* xchg = reinterpret_cast<float*>(smem + L.xchg);  // [row block][16 ch]: rank 1's sums land here (rank 0)
-  float* hold = xchg + a.nrb_max * 16;                    // [row block][16 ch]: rank 0's own sums until the peer's arrive
-
-  if (tid == 0) {
-    for (int s = 0; s < NS; ++s) {
-      mbar_init(&full[s], 33);
-      mbar_init(&empty[s], kR8Cons);
-    }
-    for (int i = 0; i < kR8Red; ++i) {
-      mbar_init(&rbfull[i], kR8Cons);
-      mbar_init(&rbfree[i], 1);
-    }
-    if (S > 1 && rank == 0) {
-      for (int rb = 0; rb < nrb; ++rb) {
-        const int nch = min(16, (o_hi - o_lo - 2 * rb) * 8);
-        mbar_init(&xch[rb], 1);
-        mbar_expect_tx(&xch[rb], (uint32_t)(nch * 4));
-      }
-    }
-    mbar_fence_init();
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  pdl_launch_dependents();
-  __syncthreads();
-  if (S > 1) cluster_arrive();
-
-  if (warp == kR8Cons) {
-    // ------------------------------------------------------------------ producer
-    const uint8_t* scb = reinterpret_cast<const uint8_t*>(a.sc);
-    const uint8_t* szb = reinterpret_cast<const uint8_t*>(a.sz);
-    int slot = 0, use = 0, rb = 0, j = 0;
-    bool waited = (S == 1);
-    RING_DBG_DECL;
-    for (int it = 0; it < items; ++it) {
-      RING_CLK(t0);
-      if (use > 0) {
-        if (!waited) cluster_wait(), waited = true;
-        mbar_wait(&empty[slot], (uint32_t)((use - 1) & 1));
-      }
-      RING_CLK(t1);
-      RING_ACC(0, t1 - t0);
-      const int g0 = kg_lo + j * kSlotGroups, ng = min(kSlotGroups, kg_hi - g0);
-      const int n0 = (o_lo + 2 * rb) * 8, nch = min(16, o_hi * 8 - n0);
-      uint8_t* sw = ring + slot * kSlotBytes;
-      if (lane == 0) {
-        const uint32_t len = (uint32_t)ng * 256u;
-        const int nq = nch >> 2;
-        mbar_expect_tx(&full[slot], (uint32_t)nq * len);
-        for (int q = 0; q < nq; ++q)
-          bulk_g2s(sw + q * kQS, a.qw + (size_t)((n0 >> 2) + q) * K + (size_t)g0 * kGroup, len, &full[slot]);
-      }
-      {
-        const int grp = lane >> 1, half = lane & 1;
-        if (grp < ng && half * 8 < nch) {
-          const size_t off = ((size_t)(g0 + grp) * N + n0 + half * 8) * 2;
-          const uint32_t dst = smem_u32(sw) + kSlotW + grp * 32 + half * 16;
-          ring_cp_async16(dst, scb + off);
-          ring_cp_async16(dst + 512, szb + off);
-        }
-      }
-      ring_cp_async_arrive(&full[slot]);
-      RING_CLK(t2);
-      RING_ACC(1, t2 - t1);
-      RING_ACC(3, 1);
-      if (++j == nsl) j = 0, ++rb;
-      if (++slot == NS) slot = 0, ++use;
-    }
-    if (!waited) cluster_wait();
-    RING_STAMP(1);
-    RING_DBG_FLUSH(18);
-    return;
-  }
-
-  if (S > 1) cluster_wait();
-  RING_STAMP(2);
-  pdl_wait_prior_grid();
-  RING_STAMP(3);
-
-  if (warp == kR8Cons + 1) {
-    // ------------------------------------------------------------------ finisher
-    // Sums the 16 warps' partials of a row block (fixed order) and frees the red slot at once.  With k split over the
-    // cluster, rank 1 pushes its sums into rank 0's shared memory; rank 0 parks its own sums and completes row
-    // blocks (add the peer's, round, store) as the peer's words arrive -- never blocking the consumers on the peer.
-    T* y = reinterpret_cast<T*>(a.y);
-    const int ch = lane & 15;
-    int fl = 0;  // rank 0, k split: next row block to complete
-    for (int rb = 0; rb < nrb; ++rb) {
-      const int rs = rb % kR8Red;
-      mbar_wait(&rbfull[rs], (uint32_t)((rb / kR8Red) & 1));
-      float v = 0.f;
-#pragma unroll
-      for (int w = 0; w < kR8Cons; ++w) v += red[(rs * kR8Cons + w) * 16 + ch];  // fixed order: deterministic
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&rbfree[rs]);
-      const int n0 = (o_lo + 2 * rb) * 8, nch = min(16, o_hi * 8 - n0);
-      if (S == 1) {
-        if (lane < nch) y[n0 + ch] = from_float<T>(v);
-      } else if (rank == 1) {
-        if (lane < nch) {
-          const uint32_t dbar = map_to_rank(smem_u32(&xch[rb]), 0);
-          const uint32_t dst = map_to_rank(smem_u32(&xchg[rb * 16 + ch]), 0);
-          asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(dst),
-                       "r"(__float_as_uint(v)), "r"(dbar)
-                       : "memory");
-        }
-      } else {
-        if (lane < 16) hold[rb * 16 + ch] = v;  // read back by the same lane only
-        while (fl <= rb) {
-          const bool ok = __all_sync(0xffffffffu, mbar_try_wait(&xch[fl], 0));
-          if (!ok) break;
-          const int f0 = (o_lo + 2 * fl) * 8, fch = min(16, o_hi * 8 - f0);
-          if (lane < fch) y[f0 + ch] = from_float<T>(hold[fl * 16 + ch] + xchg[fl * 16 + ch]);
-          ++fl;
-        }
-      }
-    }
-    if (S > 1 && rank == 0) {
-      for (; fl < nrb; ++fl) {
-        mbar_wait(&xch[fl], 0);
-        const int f0 = (o_lo + 2 * fl) * 8, fch = min(16, o_hi * 8 - f0);
-        if (lane < fch) y[f0 + ch] = from_float<T>(hold[fl * 16 + ch] + xchg[fl * 16 + ch]);
-      }
-    }
-    RING_STAMP(6);
-    return;
-  }
-
-  // -------------------------------------------------------------------- consumers: warp w owns group w of every slot
-  const int c = lane >> 2, tig = lane & 3;
-  const uint32_t xd_u32 = smem_u32(smem + L.x);
-  float2* gx = reinterpret_cast<float2*>(smem + L.xsum);  // [group][tig] {e_g 2^-7 tig (0 for tig 3), X_g for tig 0 else 0}
-  {
-    // digits of this warp's groups (exactly the ones it consumes): lane = (16-byte chunk cc = lane >> 1, half h).
-    // Every load is issued before the first use; the group's largest magnitude and the digit sums come from one
-    // REDUX each (integer warp reductions), the digits from the 1.5 * 2^23 rounding trick (no F2I on the path).
-    const T* xg = reinterpret_cast<const T*>(a.x) + (size_t)kg_lo * kGroup;
-    const int cc = lane >> 1, h = lane & 1;
-    const int m = cc >> 2, jn = cc & 3;  // 32-k block, nibble pair: even pairs are low nibbles, odd ones high
-    constexpr int kMaxOwn = 8;           // groups per warp the loads are batched for (k <= 2 * 8 * 16 * 128 per launch)
-    for (int G0 = warp; G0 < ngr; G0 += kMaxOwn * kR8Cons) {
-      uint2 xv[kMaxOwn];
-#pragma unroll
-      for (int i = 0; i < kMaxOwn; ++i) {
-        const int Gl = G0 + i * kR8Cons;
-        xv[i] = make_uint2(0u, 0u);
-        if (Gl < ngr) xv[i] = *reinterpret_cast<const uint2*>(xg + (size_t)Gl * kGroup + cc * 8 + h * 4);
-      }
-#pragma unroll
-      for (int i = 0; i < kMaxOwn; ++i) {
-        const int Gl = G0 + i * kR8Cons;
-        if (Gl >= ngr) break;
-        float f[4];
-        {
-          float2 p0, p1;
-          if constexpr (kBf16) p0 = __bfloat1622float2(u32_as_b2(xv[i].x)), p1 = __bfloat1622float2(u32_as_b2(xv[i].y));
-          else p0 = __half22float2(u32_as_h2(xv[i].x)), p1 = __half22float2(u32_as_h2(xv[i].y));
-          f[0] = p0.x, f[1] = p0.y, f[2] = p1.x, f[3] = p1.y;
-        }
-        // non-negative floats order like their bit patterns: the group's largest magnitude with one integer REDUX
-        const uint32_t am = max(max(__float_as_uint(fabsf(f[0])), __float_as_uint(fabsf(f[1]))),
-                                max(__float_as_uint(fabsf(f[2])), __float_as_uint(fabsf(f[3]))));
-        const int ex = (int)(__reduce_max_sync(0xffffffffu, am) >> 23);
-        // e = 2^(floor(log2 amax) - 5): |x| / e < 64.  Groups whose largest magnitude is below 2^-121 (bf16 only)
-        // count as zero.
-        const bool nz = ex >= 6;
-        const float inv_e = nz ? __uint_as_float((uint32_t)(259 - ex) << 23) : 0.f;
-        const float e = nz ? __uint_as_float((uint32_t)(ex - 5) << 23) : 0.f;
-        const uint32_t base = xd_u32 + (uint32_t)Gl * kR8GroupBytes + (jn & 1) * 64 + m * 4 + (jn >> 1);
-        constexpr float kMagic = 12582912.f;  // 1.5 * 2^23: (t + kMagic) holds rint(t) in its low mantissa bits
-        int s0 = 0, s1 = 0, s2 = 0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {  // value q = pair u = 2 h + (q >> 1), element q & 1 -> byte (jn >> 1) + 2 (q & 1) of word [u][m]
-          const float t = f[q] * inv_e;
-          const float a0 = t + kMagic;
-          const float r1 = (t - (a0 - kMagic)) * 128.f;
-          const float a1 = r1 + kMagic;
-          const float r2 = (r1 - (a1 - kMagic)) * 128.f;
-          const float a2 = r2 + kMagic;
-          const int d0 = __float_as_int(a0) - 0x4B400000, d1 = __float_as_int(a1) - 0x4B400000,
-                    d2 = __float_as_int(a2) - 0x4B400000;
-          s0 += d0, s1 += d1, s2 += d2;
-          const uint32_t ad = base + (2 * h + (q >> 1)) * 16 + (q & 1) * 2;
-          sts8(ad, d0);
-          sts8(ad + 128, d1);
-          sts8(ad + 256, d2);
-        }
-        // X_g = sum_k x_k from the digit sums (the digits ARE x to 2^-21 of the group's largest magnitude)
-        s0 = __reduce_add_sync(0xffffffffu, s0);
-        s1 = __reduce_add_sync(0xffffffffu, s1);
-        s2 = __reduce_add_sync(0xffffffffu, s2);
-        if (lane < 4) {
-          const float X = e * fmaf((float)s2, 6.103515625e-05f, fmaf((float)s1, 0.0078125f, (float)s0));
-          gx[Gl * 4 + lane] = make_float2(lane == 3 ? 0.f : e * (lane == 0 ? 1.f : (lane == 1 ? 0.0078125f : 6.103515625e-05f)),
-                                          lane == 0 ? X : 0.f);
-        }
-      }
-    }
-    __syncwarp();
-  }
-  RING_STAMP(4);
-
-  const int lm = lane >> 3, lg = lane & 7;
-  const uint32_t ldsm_off = (uint32_t)((lg >> 2) * kQS + (lm >> 1) * 128 + (lg & 3) * 32 + (lm & 1) * 16 + warp * 256);
-  const uint32_t ring_u32 = smem_u32(ring);
-  const bool liveH = c < 6, liveR = liveH && !(c & 1);
-  const uint32_t xd_lane = xd_u32 + (uint32_t)(c * 64 + tig * 16);
-  uint32_t Bh[4] = {0u, 0u, 0u, 0u}, Br[4] = {0u, 0u, 0u, 0u};
-  float2 gxv = make_float2(0.f, 0.f);
-  int curG = -1;
-  const int zero4[4] = {0, 0, 0, 0};
-
-  int slot = 0, use = 0;
-  RING_DBG_DECL;
-  for (int rb = 0; rb < nrb; ++rb) {
-    const int n0 = (o_lo + 2 * rb) * 8;
-    const bool two = (o_hi * 8 - n0) >= 16;
-    float y0 = 0.f, y1 = 0.f;
-    for (int j = 0; j < nsl; ++j) {
-      RING_CLK(t0);
-      mbar_wait(&full[slot], (uint32_t)(use & 1));
-      RING_CLK(t1);
-      RING_ACC(0, t1 - t0);
-      const int ng = min(kSlotGroups, ngr - j * kSlotGroups);
-      if (warp < ng && !RING_DRY) {
-        const uint32_t sb = ring_u32 + (uint32_t)slot * kSlotBytes;
-        const int Gl = j * kSlotGroups + warp;
-        uint32_t wa[4], wb[4] = {0u, 0u, 0u, 0u};
-        ldsm4(wa, sb + ldsm_off);
-        if (two) ldsm4(wb, sb + ldsm_off + 2 * kQS);
-        if (Gl != curG) {  // the digits of a group are the same for every row block: reloaded only when k moves
-          curG = Gl;
-          if (liveH) {
-            const uint4 v = lds128(xd_lane + (uint32_t)Gl * kR8GroupBytes);
-            Bh[0] = v.x, Bh[1] = v.y, Bh[2] = v.z, Bh[3] = v.w;
-          }
-          if (liveR) {
-            const uint4 v = lds128(xd_lane + (uint32_t)Gl * kR8GroupBytes);
-            Br[0] = v.x, Br[1] = v.y, Br[2] = v.z, Br[3] = v.w;
-          }
-          gxv = gx[Gl * 4 + tig];
-        }
-        const uint32_t sp = sb + kSlotW + (uint32_t)(warp * 32 + c * 2);
-        const uint16_t s_a = lds16(sp), z_a = lds16(sp + 512);
-        int accR[4], accH[4];
-        imma_16832(accR, wa[0], wb[0], wa[1], wb[1], Br[0], Br[1], zero4);
-        imma_16832(accH, wa[0] & 0xf0f0f0f0u, wb[0] & 0xf0f0f0f0u, wa[1] & 0xf0f0f0f0u, wb[1] & 0xf0f0f0f0u, Bh[0], Bh[1], zero4);
-        imma_16832(accR, wa[2], wb[2], wa[3], wb[3], Br[2], Br[3], accR);
-        imma_16832(accH, wa[2] & 0xf0f0f0f0u, wb[2] & 0xf0f0f0f0u, wa[3] & 0xf0f0f0f0u, wb[3] & 0xf0f0f0f0u, Bh[2], Bh[3], accH);
-        // this lane's columns 2 tig, 2 tig + 1 = digit tig: low-nibble sum accR[0] - accH[0], high-nibble sum accH[1] / 16
-        const float sa = bits16_to_float(s_a, kBf16), za = bits16_to_float(z_a, kBf16);
-        const float t0f = fmaf((float)accH[1], 0.0625f, (float)(accR[0] - accH[0]));
-        y0 = fmaf(za, gxv.y, fmaf(sa * gxv.x, t0f, y0));
-        if (two) {
-          const uint16_t s_b = lds16(sp + 16), z_b = lds16(sp + 528);
-          const float sbf = bits16_to_float(s_b, kBf16), zb = bits16_to_float(z_b, kBf16);
-          const float t1f = fmaf((float)accH[3], 0.0625f, (float)(accR[2] - accH[2]));
-          y1 = fmaf(zb, gxv.y, fmaf(sbf * gxv.x, t1f, y1));
-        }
-      }
-      RING_CLK(t2);
-      RING_ACC(1, t2 - t1);
-      RING_ACC(3, 1);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[slot]);
-      if (++slot == NS) slot = 0, ++use;
-    }
-    // digits live in different lanes (tig): add them, then this warp's 16 partial sums -> red[rb & 1][warp]
-    RING_CLK(t3);
-    y0 += __shfl_xor_sync(0xffffffffu, y0, 1);
-    y1 += __shfl_xor_sync(0xffffffffu, y1, 1);
-    y0 += __shfl_xor_sync(0xffffffffu, y0, 2);
-    y1 += __shfl_xor_sync(0xffffffffu, y1, 2);
-    const int rs = rb % kR8Red;
-    if (rb >= kR8Red) mbar_wait(&rbfree[rs], (uint32_t)((rb / kR8Red - 1) & 1));
-    if (tig == 0) {
-      float* r = red + (rs * kR8Cons + warp) * 16;
-      r[c] = y0;
-      r[c + 8] = y1;
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&rbfull[rs]);
-    RING_CLK(t4);
-    RING_ACC(2, t4 - t3);
-  }
-  RING_STAMP(5);
-  RING_DBG_FLUSH(warp);
-}
-
 #ifdef B200AWQ_TRACE
 extern "C" int b200awq_debug_ring_stats(long long* host) {
   return (int)cudaMemcpyFromSymbol(host, g_ring_dbg, sizeof(long long) * 80);
@@ -871,43 +526,6 @@ int launch_ring_t(const RingArgs& a, bool pdl, cudaStream_t stream) {
   return e == cudaSuccess ? 0 : (int)e;
 }
 
-int launch_ring8_t(const RingArgs& a, int dtype, bool pdl, cudaStream_t stream) {
-  static bool attr_set[2][32] = {};
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return B200AWQ_ERR_DEVICE;
-  const int ti = dtype == B200AWQ_DTYPE_F16 ? 0 : 1;
-  const void* kern = ti == 0 ? (const void*)w4a16_ring8_kernel<__half> : (const void*)w4a16_ring8_kernel<__nv_bfloat16>;
-  if (!attr_set[ti][dev & 31]) {
-    if (cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kRingSmemBudget)) return (int)e;
-    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    attr_set[ti][dev & 31] = true;
-  }
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(a.units * a.S));
-  cfg.blockDim = dim3(kR8Threads);
-  cfg.dynamicSmemBytes = (size_t)a.L.total;
-  cfg.stream = stream;
-  cudaLaunchAttribute attrs[2];
-  int na = 0;
-  if (a.S > 1) {
-    attrs[na].id = cudaLaunchAttributeClusterDimension;
-    attrs[na].val.clusterDim.x = (unsigned)a.S;
-    attrs[na].val.clusterDim.y = 1;
-    attrs[na].val.clusterDim.z = 1;
-    ++na;
-  }
-  if (pdl) {
-    attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attrs[na].val.programmaticStreamSerializationAllowed = 1;
-    ++na;
-  }
-  cfg.attrs = attrs;
-  cfg.numAttrs = na;
-  void* args[] = {const_cast<RingArgs*>(&a)};
-  cudaError_t e = cudaLaunchKernelExC(&cfg, kern, args);
-  return e == cudaSuccess ? 0 : (int)e;
-}
-
 }  // namespace
 
 int launch_ring(const void* x, const void* qw, const void* sc, const void* sz, void* y, int M, int N, int K, int dtype,
@@ -929,26 +547,19 @@ int launch_ring(const void* x, const void* qw, const void* sc, const void* sz, v
   if (nrb_max > kRingMaxRb) return B200AWQ_ERR_SHAPE;
   a.nrb_max = nrb_max;
   const int ngr = (G + a.S - 1) / a.S;
-  // arithmetic: fp16 one token -> int8 digits (MODE 8); fp16 otherwise -> group-factored fp16 MACs (MODE 2);
-  // bf16 -> operand-exact (MODE 0).  See the header comments of the two kernels.
-  int mode = (tune.mode == 0 || tune.mode == 2 || tune.mode == 8) ? tune.mode : (dtype == B200AWQ_DTYPE_F16 ? (M == 1 ? 8 : 2) : 0);
-  if (mode == 8 && M != 1) mode = dtype == B200AWQ_DTYPE_F16 ? 2 : 0;
+  // arithmetic: fp16 -> group-factored fp16 MACs (MODE 2); bf16 -> operand-exact (MODE 0).  (One fp16 token normally
+  // never gets here: w4a16_decode.cu serves it.)
+  const int mode = (tune.mode == 0 || tune.mode == 2) ? tune.mode : (dtype == B200AWQ_DTYPE_F16 ? 2 : 0);
   RingLayout& L = a.L;
   L.ngr = ngr;
   L.xrow = ngr * 256;
   int off = 0;
-  L.bars = off, off += 8 * (2 * 8 + 2 * kR8Red + kRingMaxRb);
+  L.bars = off, off += 8 * (2 * 8 + 4 + kRingMaxRb);
   off = (off + 127) & ~127;
-  if (mode == 8) {
-    L.x = off, off += ngr * kR8GroupBytes;      // digit arrays
-    L.xsum = off, off += ngr * 4 * 8;           // {e_g 2^-7 tig, X_g} per (group, tig)
-    L.red = off, off += kR8Red * kR8Cons * 16 * 4;
-  } else {
-    L.x = off, off += M * L.xrow;
-    L.xsum = off, off += 8 * ngr * 8;
-    L.red = off, off += 2 * kRingCons * 128 * 4;
-  }
-  L.xchg = off, off += (mode == 8 ? 2 * nrb_max * 16 * 4 : nrb_max * 16 * a.Mp * 4);  // mode 8: peer sums + own parked sums
+  L.x = off, off += M * L.xrow;
+  L.xsum = off, off += 8 * ngr * 8;
+  L.red = off, off += 2 * kRingCons * 128 * 4;
+  L.xchg = off, off += nrb_max * 16 * a.Mp * 4;
   off = (off + 127) & ~127;
   L.ring = off;
   int ns = (kRingSmemBudget - off) / kSlotBytes;
@@ -957,7 +568,6 @@ int launch_ring(const void* x, const void* qw, const void* sc, const void* sz, v
   if (ns < 3) return B200AWQ_ERR_SHAPE;  // activations too large next to a useful ring: the caller falls back
   a.NS = ns;
   L.total = off + ns * kSlotBytes;
-  if (mode == 8) return launch_ring8_t(a, dtype, pdl, stream);
   const bool m1 = (M == 1);
   if (dtype == B200AWQ_DTYPE_F16) {
     if (mode == 0) return m1 ? launch_ring_t<__half, 0, true>(a, pdl, stream) : launch_ring_t<__half, 0, false>(a, pdl, stream);

@@ -94,4 +94,4 @@ if M == 1:
     run("decode kernel, dry (no math)", 1, {})
     run("decode kernel, k split 2", 0, {"B200AWQ_DECODE_SPLIT": "2"})
     run("decode kernel, no k split", 0, {"B200AWQ_DECODE_SPLIT": "1"})
-run("ring, int8 digits (mode 8)", 0, {"B200AWQ_DECODE": "0"})
+run("ring kernel, fp16 MACs (w4a16_ring.cu)", 0, {"B200AWQ_DECODE": "0"})

@@ -288,7 +288,29 @@ __global__ void __launch_bounds__((CONS + 2) * 32, 2) w4a16_decode_kernel(const 
   if (S > 1) dec_cluster_arrive();  // publishes rank 0's exchange barriers to the peers
   if (S > 1) dec_cluster_wait();
   DEC_STAMP(2);
+  // Consumers: everything the first activation loads need is computed BEFORE the dependency wait, and the loads are the
+  // first instructions after it (measured: ~470 cycles passed between the wait returning and the loads issuing when the
+  // address arithmetic -- kernel parameters from the constant bank, cold instructions -- came after the wait).
+  constexpr int kMaxOwn = 32 / kDecCons;  // groups a warp converts together (k = 4096: all of its groups)
+  const int x_eoff = (lane >> 3) * 32 + ((lane >> 2) & 1) * 8 + 2 * (lane & 3);  // see the digit staging below
+  const uint32_t* xfirst[kMaxOwn];
+#pragma unroll
+  for (int i = 0; i < kMaxOwn; ++i) {
+    const int Gl = min(warp + i * kDecCons, max(ngr - 1, 0));
+    xfirst[i] = reinterpret_cast<const uint32_t*>(reinterpret_cast<const T*>(a.x) + (size_t)(kg_lo + Gl) * kGroup + x_eoff);
+  }
   pdl_wait_prior_grid();  // activations (and y) belong to the stream order from here on
+  uint32_t xa0[kMaxOwn], xb0[kMaxOwn];
+  if (warp < kDecCons) {
+#pragma unroll
+    for (int i = 0; i < kMaxOwn; ++i) {
+      asm volatile("ld.global.u32 %0, [%1];" : "=r"(xa0[i]) : "l"(xfirst[i]) : "memory");
+      asm volatile("ld.global.u32 %0, [%1 + 32];" : "=r"(xb0[i]) : "l"(xfirst[i]) : "memory");
+    }
+  }
+#ifdef B200AWQ_TRACE
+  const long long clk_wait = clock64();
+#endif
   DEC_STAMP(3);
 
   if (warp == kDecCons + 1) {
@@ -380,16 +402,31 @@ __global__ void __launch_bounds__((CONS + 2) * 32, 2) w4a16_decode_kernel(const 
     const int m = lane >> 3, par = (lane >> 2) & 1, u = lane & 3;
     const int eoff = m * 32 + par * 8 + 2 * u;                      // first pair; the second one is 16 channels further
     const uint32_t woff = (uint32_t)(par * 64 + u * 16 + m * 4);    // + digit * 128
-    constexpr int kMaxOwn = 32 / kDecCons;  // groups converted together (k = 4096: all of a warp's groups)
     uint8_t* xd = smem + L.x;
     for (int G0 = warp; G0 < ngr; G0 += kMaxOwn * kDecCons) {
       uint32_t xa[kMaxOwn], xb[kMaxOwn];
+#ifdef B200AWQ_TRACE
+      const long long ld_t0 = clock64();
+#endif
 #pragma unroll
       for (int i = 0; i < kMaxOwn; ++i) {
-        const int Gl = min(G0 + i * kDecCons, ngr - 1);  // clamped: the extra conversions are not stored
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(xg + (size_t)Gl * kGroup + eoff);
-        xa[i] = src[0], xb[i] = src[8];
+        if (G0 == warp) {  // the first batch was loaded right behind the dependency wait
+          xa[i] = xa0[i], xb[i] = xb0[i];
+        } else {
+          const int Gl = min(G0 + i * kDecCons, ngr - 1);  // clamped: the extra conversions are not stored
+          const uint32_t* src = reinterpret_cast<const uint32_t*>(xg + (size_t)Gl * kGroup + eoff);
+          xa[i] = src[0], xb[i] = src[8];
+        }
       }
+#ifdef B200AWQ_TRACE
+      if (G0 == warp && warp == 0 && blockIdx.x == 0) {  // latency of the first activation loads of warp 0 (cycles)
+        const uint32_t dep = xa[0] ^ xb[0] ^ xa[kMaxOwn - 1] ^ xb[kMaxOwn - 1];
+        long long ld_t1 = dep == 0x9e3779b9u ? 1 : 0;  // a real dependency: the clock below is read after the data arrived
+        asm volatile("" ::"l"(ld_t1) : "memory");
+        ld_t1 += clock64();
+        if (lane == 0) g_ring_dbg[19 * 4 + 2] = ld_t1 - ld_t0, g_ring_dbg[19 * 4 + 3] = ld_t0 - clk_wait;
+      }
+#endif
 #pragma unroll
       for (int i = 0; i < kMaxOwn; ++i) {
         const int Gl = G0 + i * kDecCons;

@@ -80,7 +80,8 @@ def run(tag, flags, env):
     assert lib.b200awq_debug_ring_stats(st) == 0
     st = list(st)
     if st[77] > 0:
-        print(f"   SM clock over the producer's loop: {st[76]} cycles in {st[77]} ns = {st[76] / st[77] * 1e3:.0f} MHz")
+        print(f"   SM clock over the producer's loop: {st[76]} cycles in {st[77]} ns = {st[76] / st[77] * 1e3:.0f} MHz;"
+              f"  warp 0: dependency wait -> first activation loads issued {st[79]} cycles, issue -> data {st[78]} cycles")
     for w in range(19):
         a, b, c, n = st[4 * w:4 * w + 4]
         role = "producer" if w == 18 else f"warp {w}"

@@ -179,7 +179,8 @@ torch::Tensor single_query_attention(const torch::Tensor q, const torch::Tensor 
   const c10::cuda::CUDAGuard guard(q.device());
   torch::Tensor out = torch::empty({batch_size, nheads, headdim}, q.options());
   // one zero-initialised workspace per (device, stream); the kernels leave it zero where it matters
-  static std::map<std::pair<int, void*>, torch::Tensor> workspaces;
+  // (leaked on purpose: CUDA tensors must not be destroyed by static destructors at interpreter exit)
+  static auto& workspaces = *new std::map<std::pair<int, void*>, torch::Tensor>();
   const size_t need = b200awq_single_query_attention_workspace_bytes(batch_size, nheads, nheads_kv, headdim, memory_max_seqlen);
   void* st = at::cuda::getCurrentCUDAStream().stream();
   auto key = std::make_pair((int)q.get_device(), st);

@@ -692,7 +692,7 @@ def run_reference(args):
     v = 1.0 / (dt * LLAMA3_8B["layers"])
     sample = "each step = 1 of 32 decoder layers (5 WQLinear forwards, M=1, dequant every call); tok/s = 1/(32 x step time)"
     print(json.dumps({
-        "impl": "reference", "metric": METRIC % 1, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": max(args.warmup, 1),
+        "impl": "reference", "metric": METRIC % max(int(args.gpus), 1), "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": max(args.warmup, 1),
         "ms_per_step": dt * 1e3, "steps_per_token": LLAMA3_8B["layers"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32",
         "data": "synthetic", "config": {"workload": "Llama-3-8B W4A16 g128 decode bs=1 (BASELINE configs[1]), CPU pure-PyTorch dequant path",

@@ -28,7 +28,7 @@ print("%-110s %6s  %s" % ("kernel", "instr", "  ".join(MNEM)))
 for name, lines in funcs.items():
     text = "\n".join(lines)
     counts = [len(re.findall(r"\b%s[.\w]*" % m, text)) for m in MNEM]
-    short = re.sub(r"\(.*", "", name).replace("b200awq::", "")
+    short = re.sub(r"\(.*", "", name.replace("(anonymous namespace)::", "")).replace("b200awq::", "")
     print("%-110s %6d  %s" % (short[:110], len(lines), "  ".join("%*d" % (len(m), c) for m, c in zip(MNEM, counts))))
 # inner loop of the one-token decode kernel (16 consumer warps, fp16): from the first LDSM to the loop branch
 for name, lines in funcs.items():

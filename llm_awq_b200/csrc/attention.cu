@@ -136,18 +136,26 @@ __global__ void __launch_bounds__(kAttThreads) single_query_attention_kernel(con
     float acc[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) acc[g] = 0.f;
-    for (int c = 0; c < nch; ++c) {
-      const uint4 kv = *reinterpret_cast<const uint4*>(kc + ((size_t)c * L + slot) * 8);
-      float kf[8];
-      unpack8<T>(kv, kf);
+    for (int c0 = 0; c0 < nch; c0 += 4) {  // four 16-byte loads in flight per position; the tail is guarded
+      uint4 kv4[4];
 #pragma unroll
-      for (int g = 0; g < G; ++g) {
-        const float4 qa = *reinterpret_cast<const float4*>(qs + g * D + c * 8);
-        const float4 qb = *reinterpret_cast<const float4*>(qs + g * D + c * 8 + 4);
-        acc[g] = fmaf(qa.x, kf[0], acc[g]), acc[g] = fmaf(qa.y, kf[1], acc[g]);
-        acc[g] = fmaf(qa.z, kf[2], acc[g]), acc[g] = fmaf(qa.w, kf[3], acc[g]);
-        acc[g] = fmaf(qb.x, kf[4], acc[g]), acc[g] = fmaf(qb.y, kf[5], acc[g]);
-        acc[g] = fmaf(qb.z, kf[6], acc[g]), acc[g] = fmaf(qb.w, kf[7], acc[g]);
+      for (int j = 0; j < 4; ++j)
+        kv4[j] = c0 + j < nch ? *reinterpret_cast<const uint4*>(kc + ((size_t)(c0 + j) * L + slot) * 8) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (c0 + j >= nch) break;
+        const int c = c0 + j;
+        float kf[8];
+        unpack8<T>(kv4[j], kf);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const float4 qa = *reinterpret_cast<const float4*>(qs + g * D + c * 8);
+          const float4 qb = *reinterpret_cast<const float4*>(qs + g * D + c * 8 + 4);
+          acc[g] = fmaf(qa.x, kf[0], acc[g]), acc[g] = fmaf(qa.y, kf[1], acc[g]);
+          acc[g] = fmaf(qa.z, kf[2], acc[g]), acc[g] = fmaf(qa.w, kf[3], acc[g]);
+          acc[g] = fmaf(qb.x, kf[4], acc[g]), acc[g] = fmaf(qb.y, kf[5], acc[g]);
+          acc[g] = fmaf(qb.z, kf[6], acc[g]), acc[g] = fmaf(qb.w, kf[7], acc[g]);
+        }
       }
     }
 #pragma unroll
@@ -206,15 +214,25 @@ __global__ void __launch_bounds__(kAttThreads) single_query_attention_kernel(con
 #pragma unroll
     for (int e = 0; e < 8; ++e) o[g][e] = 0.f;
   if (r < rows) {
-    for (int p = p0 + r; p < p1; p += rows) {
-      const uint4 vv = *reinterpret_cast<const uint4*>(vc + (size_t)(p % L) * D + dc * 8);
-      float vf[8];
-      unpack8<T>(vv, vf);
+    for (int pb = p0 + r; pb < p1; pb += 4 * rows) {  // four rows of V in flight per thread
+      uint4 vv[4];
 #pragma unroll
-      for (int g = 0; g < G; ++g) {
-        const float pr = sc[g * a.chunk + (p - p0)];
+      for (int j = 0; j < 4; ++j) {
+        const int p = pb + j * rows;
+        vv[j] = p < p1 ? *reinterpret_cast<const uint4*>(vc + (size_t)(p % L) * D + dc * 8) : make_uint4(0u, 0u, 0u, 0u);
+      }
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[g][e] = fmaf(pr, vf[e], o[g][e]);
+      for (int j = 0; j < 4; ++j) {
+        const int p = pb + j * rows;
+        if (p >= p1) break;
+        float vf[8];
+        unpack8<T>(vv[j], vf);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const float pr = sc[g * a.chunk + (p - p0)];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[g][e] = fmaf(pr, vf[e], o[g][e]);
+        }
       }
     }
   }
@@ -358,7 +376,7 @@ int launch_single_query_attention(const void* q, const void* k, const void* v, v
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
   const int chunk_cap = std::max(256, (48 * 1024 / 4) / G / 32 * 32);  // logits of a chunk: G * chunk floats <= 48 KB
   int splits = std::max(1, std::min(64, 2 * nsm / std::max(1, batch * kv_heads)));
-  splits = std::min(splits, (npos_max + 255) / 256);                  // >= 256 positions per CTA
+  splits = std::min(splits, (npos_max + 127) / 128);                  // >= 128 positions per CTA
   splits = std::max(splits, (npos_max + chunk_cap - 1) / chunk_cap);
   if (splits > 64) return B200AWQ_ERR_SHAPE;
   a.splits = std::max(1, splits);

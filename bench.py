@@ -520,7 +520,12 @@ def tp70b_measure(torch, dist, rank, world, device, steps, warmup):
     if world > 1:
         ms_nccl, _ = timed_steps(torch, dist, device, graph("nccl").replay, steps, warmup)
         ms_fused, _ = timed_steps(torch, dist, device, graph("fused").replay, steps, warmup)
-    ms_full = ms_nc if world == 1 else min(ms_nccl, ms_fused)
+        # the exchange's watchdog poisons the outputs with NaN when a peer never delivered: such a timing is void
+        bad = torch.tensor([0 if all(bool(torch.isfinite(y).all()) for y in ys.values()) else 1], device=device)
+        dist.all_reduce(bad)
+        if int(bad.item()):
+            ms_fused = None
+    ms_full = ms_nc if world == 1 else (ms_nccl if ms_fused is None else min(ms_nccl, ms_fused))
     if rank != 0:
         return None
     step_ms = ms_full / steps
@@ -536,7 +541,7 @@ def tp70b_measure(torch, dist, rank, world, device, steps, warmup):
         "comm": {"ms_per_step_without_allreduce": ms_nc / steps,
                  "ms_per_step_nccl_allreduce": None if ms_nccl is None else ms_nccl / steps,
                  "ms_per_step_fused_nvlink_exchange": None if ms_fused is None else ms_fused / steps,
-                 "headline_uses": "single GPU" if world == 1 else ("fused" if ms_fused <= ms_nccl else "nccl")},
+                 "headline_uses": "single GPU" if world == 1 else ("fused" if ms_fused is not None and ms_fused <= ms_nccl else "nccl")},
         "gpu_launches": len(model) * steps,
         "roofline": {"bound": "hbm", "achieved": bytes_rank / (step_ms * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
                      "frac": bytes_rank / (step_ms * 1e-3) / 1e9 / peaks["hbm"], "traffic": None, "per": "rank",

@@ -44,14 +44,21 @@
 namespace b200awq {
 
 
-#ifdef B200AWQ_TRACE
-// Debug build only (scripts/trace_chain.py): wall-clock stamps of the first and last CTA of each launch.
-__device__ unsigned long long g_trace_buf[1024 * 2 * 8];  // shared with w4a16_flat.cu (needs -rdc)
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+
+// Watchdog of the fused exchange (below): a rank whose peer never delivers (peer died, mismatched launch sequence)
+// gives up after kExchangeTimeoutNs, poisons its outputs with NaN and marks the exchange dead for the rest of the
+// process, so that a broken job produces visibly wrong numbers quickly instead of spinning on the GPU for ever.
+constexpr unsigned long long kExchangeTimeoutNs = 10ull * 1000 * 1000 * 1000;
+__device__ unsigned int g_exchange_dead = 0;
+
+#ifdef B200AWQ_TRACE
+// Debug build only (scripts/trace_chain.py): wall-clock stamps of the first and last CTA of each launch.
+__device__ unsigned long long g_trace_buf[1024 * 2 * 8];  // shared with w4a16_flat.cu (needs -rdc)
 #define B200AWQ_STAMP(ev)                                                     \
   if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) \
   g_trace_buf[(((unsigned)seq & 1023u) * 2 + (blockIdx.x != 0)) * 8 + (ev)] = globaltimer_ns()
@@ -424,6 +431,8 @@ w4a16_stream_kernel(const T* __restrict__ x, const uint16_t* __restrict__ qw, co
           asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(pa.data[r] + off), "l"(word) : "memory");
       }
     }
+    const unsigned long long t_exchange = globaltimer_ns();
+    bool dead = *(volatile unsigned int*)&g_exchange_dead != 0u;
     for (int e = tid; e < TT * 128; e += kStreamThreads) {
       const int t = e >> 7, row = (e >> 3) & 15, tok = 8 * t + (e & 7);
       if (tok < M && row < R) {
@@ -432,11 +441,18 @@ w4a16_stream_kernel(const T* __restrict__ x, const uint16_t* __restrict__ qw, co
         for (int r = 0; r < W; ++r) {  // fixed rank order: bit-identical results on every rank
           const unsigned long long* srcp =
               pa.data[pa.rank] + (size_t)((ep & 1u) * W + r) * pa.cap + (size_t)(n0 + row) * pa.tok_cap + tok;
-          unsigned long long word;
-          do {
+          unsigned long long word = 0;
+          unsigned int polls = 0;
+          while (!dead) {
             asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(word) : "l"(srcp) : "memory");
-          } while ((unsigned int)(word >> 32) != ep);
-          v += __uint_as_float((unsigned int)word);
+            if ((unsigned int)(word >> 32) == ep) break;
+            if ((++polls & 0xfffu) == 0u &&
+                (globaltimer_ns() - t_exchange > kExchangeTimeoutNs || *(volatile unsigned int*)&g_exchange_dead != 0u)) {
+              dead = true;
+              atomicExch(&g_exchange_dead, 1u);
+            }
+          }
+          v += dead ? __uint_as_float(0x7fc00000u) : __uint_as_float((unsigned int)word);
         }
         y[(size_t)tok * N + n0 + row] = from_float<T>(v);
       }

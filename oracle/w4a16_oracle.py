@@ -144,8 +144,11 @@ def rn_bf16(x: np.ndarray) -> np.ndarray:
 
 
 def rounder(dtype: str):
+    """Round-to-nearest-even into ``dtype``; "f64" = no rounding (the unrounded restatement, used where a fixture
+    was produced by the reference's fp32 / fp64 Python)."""
     return {"f16": rn_f16, "fp16": rn_f16, "half": rn_f16,
-            "bf16": rn_bf16, "bfloat16": rn_bf16}[dtype]
+            "bf16": rn_bf16, "bfloat16": rn_bf16,
+            "f64": lambda v: np.asarray(v, dtype=np.float64)}[dtype]
 
 
 # --------------------------------------------------------------------------------------

@@ -71,6 +71,67 @@ def repacker_golden():
     print("wrote reference_repacker.npz", len(out), "arrays")
 
 
+def layer_ops_golden():
+    """tests/golden/reference_layer_ops.npz: what the reference's own PYTHON statements of the ops around the linears
+    give on CPU -- for oracle/layer_oracle.py.  The kernels themselves are CUDA-only; these are the definitions the
+    reference keeps beside them:
+      * RMSNorm._norm * weight                       tinychat/models/llama.py:24-31
+      * precompute_freqs_cis + apply_rotary_emb      tinychat/models/llama.py:39-47, 68-84 (pairs (i, i + d/2))
+      * precompute_freqs                             tinychat/models/llama.py:50-57 (table for fused_rope_with_pos)
+      * the KV-cache store and the softmax attention of the prefill branch
+                                                     tinychat/modules/fused_attn.py:256-305 (restated below with the
+                                                     same tensor expressions: the module itself needs CUDA caches)
+    Inputs hold fp16-representable values; everything is computed in fp32 / fp64 and stored unrounded."""
+    sys.modules.setdefault("awq_inference_engine", types.ModuleType("awq_inference_engine"))
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    import contextlib
+    import math
+    with contextlib.redirect_stdout(sys.stderr):
+        import tinychat.models.llama as L
+    g = torch.Generator().manual_seed(4242)
+    out = {}
+    # --- RMSNorm
+    for idx, (rows, dim, eps) in enumerate([(3, 64, 1e-6), (5, 4096, 1e-5), (2, 200, 1e-6)]):
+        x = torch.randn(rows, dim, generator=g).half().double() * 3
+        w = (1 + 0.1 * torch.randn(dim, generator=g)).half().double()
+        norm = L.RMSNorm(dim, eps=eps).double()
+        with torch.no_grad():
+            norm.weight.copy_(w)
+            y = norm._norm(x) * norm.weight
+        out[f"n{idx}_x"], out[f"n{idx}_w"], out[f"n{idx}_eps"], out[f"n{idx}_y"] = x.numpy(), w.numpy(), np.float64(eps), y.numpy()
+    # --- RoPE + one decode step seen as the last row of a prefill
+    for idx, (S, H, Hkv, D, theta, scale) in enumerate([(9, 4, 2, 16, 10000.0, 1.0), (17, 8, 8, 32, 500000.0, 0.5),
+                                                         (12, 8, 2, 64, 10000.0, 1.0)]):
+        xq = torch.randn(1, S, H, D, generator=g).half().float()
+        xk = torch.randn(1, S, Hkv, D, generator=g).half().float()
+        xv = torch.randn(1, S, Hkv, D, generator=g).half().float()
+        fc = L.precompute_freqs_cis(D, S, theta, scale)
+        rq, rk = L.apply_rotary_emb(xq, xk, freqs_cis=fc)
+        # the table the callers hand to fused_rope_with_pos (llama.py:312-317 passes the scale, precompute_freqs :50-57
+        # does not use it: the table is always unscaled) and what that table means in terms of apply_rotary_emb
+        table = L.precompute_freqs(D, S, theta, scale)  # [S, 1, 1, D]
+        rq1, rk1 = L.apply_rotary_emb(xq, xk, freqs_cis=L.precompute_freqs_cis(D, S, theta, 1.0))
+        # cache store, fused_attn.py:262-270
+        keys_store = rk.reshape(1, S, Hkv, D // 8, 8).permute(0, 2, 3, 1, 4).contiguous()   # [B, Hkv, D/8, S, 8]
+        values_store = xv.transpose(2, 1).contiguous()                                       # [B, Hkv, S, D]
+        # attention, fused_attn.py:290-304, fp32, causal: the last row sees every position
+        rep = H // Hkv
+        keys = torch.repeat_interleave(rk, dim=2, repeats=rep).transpose(1, 2)
+        values = torch.repeat_interleave(xv, dim=2, repeats=rep).transpose(1, 2)
+        q_ = rq.transpose(1, 2)
+        scores = torch.matmul(q_.double(), keys.double().transpose(2, 3)) / math.sqrt(D)
+        mask = torch.full((S, S), float("-inf")).triu(1).double()
+        scores = torch.softmax(scores + mask, dim=-1)
+        o = torch.matmul(scores, values.double()).transpose(1, 2)                            # [B, S, H, D]
+        for k, v in dict(xq=xq, xk=xk, xv=xv, rq=rq, rk=rk, rq1=rq1, rk1=rk1, table=table.reshape(S, D), cache_k=keys_store,
+                         cache_v=values_store, out=o).items():
+            out[f"a{idx}_{k}"] = v.double().numpy()
+        out[f"a{idx}_cfg"] = np.array([S, H, Hkv, D, theta, scale], dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, "reference_layer_ops.npz"), **out)
+    print("wrote reference_layer_ops.npz", len(out), "arrays")
+
+
 def main():
     qmodule, pseudo_quantize_tensor = _import_reference()
     g = torch.Generator().manual_seed(20260922)
@@ -150,3 +211,4 @@ def main():
 if __name__ == "__main__":
     main()
     repacker_golden()
+    layer_ops_golden()

@@ -81,7 +81,8 @@ size_t b200awq_w4a16_gemm_workspace_bytes(int m, int n, int k);
  *             DIFFERENT n (<= n_max) may share one set of buffers.
  *   1 <= m <= 8, world <= 8.  n > n_max or m > cap_words / n_max is rejected with B200AWQ_ERR_PEERS.  All ranks
  *   must issue the same sequence of calls on these buffers.  Safe under CUDA-graph capture / replay (no
- *   host-side state). */
+ *   host-side state).  A rank whose peer delivers nothing for 10 s gives up: its outputs of that call are NaN and
+ *   every later exchange of the process returns NaN at once (the kernel never spins for ever). */
 typedef struct b200awq_peers {
   void* data[8];
   void* epoch;

@@ -152,6 +152,21 @@ size_t b200awq_single_query_attention_workspace_bytes(int batch, int heads, int 
 int b200awq_rope_with_pos(const void* x, const float* freqs, void* y, int s, int b, int h, int d, int d2,
                           const long long in_strides[4], const long long out_strides[4], int dtype, void* stream);
 
+/* In-place NeoX-style RoPE on query and key from a table of cosines and sines (the HF-attention branch).  Replaces
+ *   rotary_embedding_neox(positions, query, key, head_size, cos_sin_cache)
+ *   reference: awq/kernels/csrc/position_embedding/pos_encoding_kernels.cu:13-88, csrc/pybind.cpp:24, called from
+ *              tinychat/modules/fused_attn.py:61-79 (QuantLlamaRotaryEmbedding, table built at :43-59).
+ * For every token t and head: with p = positions[t] (int64) and row = cos_sin_cache[p] ([rot_dim] of T: rot_dim / 2
+ * cosines, then rot_dim / 2 sines), the pairs (x, y) = (head[r], head[rot_dim / 2 + r]), r < rot_dim / 2, become
+ * (x cos_r - y sin_r, y cos_r + x sin_r); elements beyond rot_dim are untouched.  Products in fp32, one rounding to T
+ * (the reference multiplies and adds in T: <= 2 ulp apart).  query [tokens, q_heads, head_size] and key
+ * [tokens, k_heads, head_size] with token strides in ELEMENTS; the reference rotates key with query's head count
+ * (pos_encoding_kernels.cu:61,64 -- equal for the models that take this branch), here each tensor has its own;
+ * key may be NULL with k_heads == 0.  positions are not range-checked (as in the reference). */
+int b200awq_rotary_embedding_neox(const long long* positions, void* query, void* key, const void* cos_sin_cache, int tokens,
+                                  int q_heads, int k_heads, int head_size, int rot_dim, long long q_token_stride,
+                                  long long k_token_stride, int dtype, void* stream);
+
 /* Names used by BASELINE.json's north_star; identical to the two launchers above. */
 int gemv_forward_4bit(const void* x, const void* qweight, const void* scales, const void* szeros,
                       void* y, int m, int n, int k, int group_size, int dtype, void* stream);

@@ -257,6 +257,18 @@ int b200awq_rope_with_pos(const void* x, const float* freqs, void* y, int s, int
   return r;
 }
 
+int b200awq_rotary_embedding_neox(const long long* positions, void* query, void* key, const void* cos_sin_cache, int tokens,
+                                  int q_heads, int k_heads, int head_size, int rot_dim, long long q_token_stride,
+                                  long long k_token_stride, int dtype, void* stream) {
+  if (dtype != B200AWQ_DTYPE_F16 && dtype != B200AWQ_DTYPE_BF16) return B200AWQ_ERR_DTYPE;
+  if (!positions || !cos_sin_cache || (q_heads > 0 && !query) || (k_heads > 0 && !key)) return B200AWQ_ERR_ALIGN;
+  if (int e = check_device()) return e;
+  const int r = b200awq::launch_rope_neox(positions, query, key, cos_sin_cache, tokens, q_heads, k_heads, head_size, rot_dim,
+                                          q_token_stride, k_token_stride, dtype, pdl_enabled(), static_cast<cudaStream_t>(stream));
+  if (r == 0 && tokens > 0 && q_heads + k_heads > 0) g_launches.fetch_add(1, std::memory_order_relaxed);
+  return r;
+}
+
 int b200awq_rmsnorm(const void* x, const void* gamma, void* y, int m, int n, float eps, int dtype, void* stream) {
   if (dtype != B200AWQ_DTYPE_F16 && dtype != B200AWQ_DTYPE_BF16) return B200AWQ_ERR_DTYPE;
   if (m < 0 || n < 1) return B200AWQ_ERR_SHAPE;

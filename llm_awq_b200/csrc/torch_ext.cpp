@@ -215,6 +215,30 @@ at::Tensor fused_rope_with_pos_forward_func(const at::Tensor& input, const at::T
   return output;
 }
 
+// reference: awq/kernels/csrc/position_embedding/pos_encoding_kernels.cu:56-88 (in place, returns nothing)
+void rotary_embedding_neox(at::Tensor& positions, at::Tensor& query, at::Tensor& key, int head_size, at::Tensor& cos_sin_cache) {
+  TORCH_CHECK(positions.is_cuda() && query.is_cuda() && key.is_cuda() && cos_sin_cache.is_cuda(), "all tensors must be CUDA tensors");
+  TORCH_CHECK(positions.scalar_type() == at::ScalarType::Long && positions.is_contiguous(), "positions must be contiguous int64");
+  const int dt = dtype_code(query, "rotary_embedding_neox");
+  TORCH_CHECK(key.scalar_type() == query.scalar_type() && cos_sin_cache.scalar_type() == query.scalar_type(),
+              "query, key and cos_sin_cache must have one dtype");
+  TORCH_CHECK(query.is_contiguous() && key.is_contiguous() && cos_sin_cache.is_contiguous(), "tensors must be contiguous");
+  TORCH_CHECK(query.dim() >= 3 && key.dim() >= 3 && cos_sin_cache.dim() == 2, "query / key [b, tokens, ..., heads, head_size]");
+  TORCH_CHECK(query.size(-1) == head_size && key.size(-1) == head_size, "last dimension must be head_size");
+  const int64_t tokens = query.size(0) * query.size(1);  // reference :63
+  const int64_t q_heads = query.size(-2), k_heads = key.size(-2);
+  const int64_t rot_dim = cos_sin_cache.size(1);         // reference :64
+  TORCH_CHECK(query.numel() == tokens * q_heads * head_size && key.numel() == tokens * k_heads * head_size,
+              "query / key must hold tokens x heads x head_size elements");
+  TORCH_CHECK(positions.numel() >= tokens, "one position per token");
+  const c10::cuda::CUDAGuard guard(query.device());
+  raise(b200awq_rotary_embedding_neox(reinterpret_cast<const long long*>(positions.data_ptr<int64_t>()), query.data_ptr(),
+                                      key.data_ptr(), cos_sin_cache.data_ptr(), (int)tokens, (int)q_heads, (int)k_heads,
+                                      head_size, (int)rot_dim, q_heads * head_size, k_heads * head_size, dt,
+                                      at::cuda::getCurrentCUDAStream().stream()),
+        false);
+}
+
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "B200-native drop-in for llm-awq's awq_inference_engine (W4A16 path only)";
   m.def("gemm_forward_cuda_new", &gemm_forward_cuda_new, "New quantized GEMM kernel.");
@@ -226,6 +250,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("rotary_scale") = 1.0f, py::arg("neox_rotary_style") = true);
   m.def("fused_rope_with_pos_forward_func", &fused_rope_with_pos_forward_func,
         "Fused rope forward function with B,S,D embedding");
+  m.def("rotary_embedding_neox", &rotary_embedding_neox, "Apply GPT-NeoX style rotary embedding to query and key");
   m.def("mlp_front_forward_cuda", &mlp_front_forward_cuda, "silu(x Wgate^T) * (x Wup^T) for W4A16 weights, one call");
   m.def("set_pdl", [](bool on) { return b200awq_set_pdl(on ? 1 : 0) != 0; }, "programmatic dependent launch on/off");
   m.def("launch_count", []() { return b200awq_launch_count(); }, "kernels launched by libb200awq so far");

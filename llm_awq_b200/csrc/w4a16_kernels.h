@@ -96,6 +96,10 @@ int launch_single_query_attention(const void* q, const void* k, const void* v, v
                                   int neox, int dtype, void* workspace, size_t workspace_bytes, bool pdl, cudaStream_t stream);
 int launch_rope_with_pos(const void* x, const float* freqs, void* y, int s, int b, int h, int d, int d2, const long long* in_strides,
                          const long long* out_strides, int dtype, bool pdl, cudaStream_t stream);
+// in-place NeoX RoPE from a cos|sin table (rope_neox.cu)
+int launch_rope_neox(const long long* positions, void* query, void* key, const void* cos_sin, int tokens, int q_heads,
+                     int k_heads, int head_size, int rot_dim, long long q_stride, long long k_stride, int dtype, bool pdl,
+                     cudaStream_t stream);
 
 // tcgen05 skinny-batch kernel, 1 <= M <= 64, N % 128 == 0 (w4a16_flat.cu)
 int launch_flat(const void* x, const void* qw, const void* sc, const void* sz, void* y, int M, int N, int K, int dtype,

@@ -45,6 +45,8 @@ def lib() -> ctypes.CDLL:
         L.b200awq_single_query_attention_workspace_bytes.restype = sz
         L.b200awq_rope_with_pos.argtypes = [vp, vp, vp, ci, ci, ci, ci, ci, vp, vp, ci, vp]
         L.b200awq_rope_with_pos.restype = ci
+        L.b200awq_rotary_embedding_neox.argtypes = [vp, vp, vp, vp, ci, ci, ci, ci, ci, ctypes.c_longlong, ctypes.c_longlong, ci, vp]
+        L.b200awq_rotary_embedding_neox.restype = ci
         L.b200awq_rmsnorm.argtypes = [vp, vp, vp, ci, ci, ctypes.c_float, ci, vp]
         L.b200awq_rmsnorm.restype = ci
         L.b200awq_set_pdl.argtypes = [ci]

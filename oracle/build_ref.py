@@ -1,6 +1,7 @@
 """Build oracle/_ref/ref_awq_engine*.so: the REFERENCE's own W4A16 kernels for sm_100a.
 
-Compiles awq/kernels/csrc/quantization_new/{gemv/gemv_cuda.cu,gemm/gemm_cuda.cu} and layernorm/layernorm.cu from
+Compiles awq/kernels/csrc/quantization_new/{gemv/gemv_cuda.cu,gemm/gemm_cuda.cu}, layernorm/layernorm.cu and
+position_embedding/pos_encoding_kernels.cu from
 where they lie under /root/reference (nothing is copied into this repo) with the
 reference's nvcc flags (awq/kernels/setup.py:7-21) plus an explicit sm_100a gencode,
 and links them with oracle/ref_binding.cpp.  Output goes to oracle/_ref/ (git-ignored,
@@ -31,7 +32,8 @@ def build(force: bool = False) -> str | None:
         return TARGET if os.path.exists(TARGET) else None
     srcs = [os.path.join(CSRC, "quantization_new/gemv/gemv_cuda.cu"),
             os.path.join(CSRC, "quantization_new/gemm/gemm_cuda.cu"),
-            os.path.join(CSRC, "layernorm/layernorm.cu")]
+            os.path.join(CSRC, "layernorm/layernorm.cu"),
+            os.path.join(CSRC, "position_embedding/pos_encoding_kernels.cu")]
     bind = os.path.join(HERE, "ref_binding.cpp")
     if not force and os.path.exists(TARGET) and all(
             os.path.getmtime(TARGET) > os.path.getmtime(s) for s in srcs + [bind, __file__]):
@@ -48,12 +50,13 @@ def build(force: bool = False) -> str | None:
             "--expt-relaxed-constexpr", "--expt-extended-lambda", "--use_fast_math",
             "-Xcompiler", "-fPIC", "-w"] + common + inc
     objs = [os.path.join(OUT, "gemv_cuda.o"), os.path.join(OUT, "gemm_cuda.o"), os.path.join(OUT, "layernorm.o"),
-            os.path.join(OUT, "ref_binding.o")]
+            os.path.join(OUT, "pos_encoding_kernels.o"), os.path.join(OUT, "ref_binding.o")]
     cmds = [nvcc + ["-c", srcs[0], "-o", objs[0]],
             nvcc + ["-c", srcs[1], "-o", objs[1]],
             nvcc + ["-c", srcs[2], "-o", objs[2]],
-            ["g++", "-O2", "-std=c++17", "-fPIC", "-w"] + common + inc + ["-c", bind, "-o", objs[3]]]
-    with ThreadPoolExecutor(4) as ex:
+            nvcc + ["-c", srcs[3], "-o", objs[3]],
+            ["g++", "-O2", "-std=c++17", "-fPIC", "-w"] + common + inc + ["-c", bind, "-o", objs[4]]]
+    with ThreadPoolExecutor(5) as ex:
         for r in ex.map(lambda c: subprocess.run(c, capture_output=True, text=True), cmds):
             if r.returncode != 0:
                 raise RuntimeError("reference build failed:\n" + r.stderr[-4000:])

@@ -135,3 +135,35 @@ def rope_with_pos(x: np.ndarray, freqs: np.ndarray, dtype: str = "f16") -> np.nd
     rot = np.concatenate([-xr[..., d2 // 2:], xr[..., : d2 // 2]], axis=-1)
     y[..., :d2] = xr * np.cos(f) + rot * np.sin(f)
     return O.rounder(dtype)(y)
+
+
+def neox_cos_sin_cache(dim: int, max_position: int, base: float = 10000.0, dtype: str = "f16") -> np.ndarray:
+    """``QuantLlamaRotaryEmbedding._set_cos_sin_cache`` (tinychat/modules/fused_attn.py:26-59): row p =
+    [cos(p f_0) .. cos(p f_{dim/2-1}), sin(p f_0) .. sin(p f_{dim/2-1})] with f_i = base ** (-2 i / dim), computed in
+    fp32 by the reference and stored as fp16 (:59); here float64, rounded to ``dtype``."""
+    inv = 1.0 / np.power(float(base), np.arange(0, dim, 2, dtype=np.float64) / dim)
+    ang = np.outer(np.arange(max_position, dtype=np.float64), inv)
+    return O.rounder(dtype)(np.concatenate([np.cos(ang), np.sin(ang)], axis=-1))
+
+
+def rotary_embedding_neox(positions, query, key, head_size: int, cos_sin_cache, dtype: str = "f16"):
+    """``rotary_embedding_neox`` (awq/kernels/csrc/position_embedding/pos_encoding_kernels.cu:13-88): query / key
+    [tokens, heads, head_size] (any leading shape with tokens * heads * head_size elements), positions [tokens],
+    cos_sin_cache [max_position, rot_dim].  Per token and head, pair r < rot_dim / 2 (:33-36):
+    x' = x cos_r - y sin_r, y' = y cos_r + x sin_r with x = head[r], y = head[rot_dim / 2 + r] (:44-52); the rest of the
+    head is untouched.  Returns NEW arrays (the kernel works in place); float64 products, one rounding to ``dtype``
+    (the reference rounds after every operation of T: <= 2 ulp of T away)."""
+    pos = np.asarray(positions).reshape(-1)
+    cache = np.asarray(cos_sin_cache, dtype=np.float64)
+    rot = cache.shape[1]
+    e = rot // 2
+    rn = O.rounder(dtype)
+    outs = []
+    for t in (query, key):
+        a = np.array(t, dtype=np.float64)
+        v = a.reshape(len(pos), -1, head_size)
+        c, s = cache[pos][:, None, :e], cache[pos][:, None, e:rot]
+        x, y = v[..., :e].copy(), v[..., e:rot].copy()
+        v[..., :e], v[..., e:rot] = rn(x * c - y * s), rn(y * c + x * s)
+        outs.append(v.reshape(a.shape))
+    return outs[0], outs[1]

@@ -128,6 +128,23 @@ def layer_ops_golden():
                          cache_v=values_store, out=o).items():
             out[f"a{idx}_{k}"] = v.double().numpy()
         out[f"a{idx}_cfg"] = np.array([S, H, Hkv, D, theta, scale], dtype=np.float64)
+    # --- the cos|sin table of the HF-attention branch (rotary_embedding_neox's input), fused_attn.py:25-59, and what the
+    # rotation means in terms of apply_rotary_emb at the same positions
+    with contextlib.redirect_stdout(sys.stderr):
+        import tinychat.modules.fused_attn as FA
+    for idx, (dim, maxpos, base, heads) in enumerate([(16, 64, 10000, 4), (64, 300, 10000, 3), (128, 512, 10000, 2)]):
+        rot = FA.QuantLlamaRotaryEmbedding(dim, max_position_embeddings=maxpos, base=base, device="cpu")
+        pos = torch.randint(0, maxpos, (11,), generator=g)
+        pos[0], pos[1] = 0, maxpos - 1
+        xq = torch.randn(1, 11, heads, dim, generator=g).half().float()
+        xk = torch.randn(1, 11, heads, dim, generator=g).half().float()
+        fc = L.precompute_freqs_cis(dim, maxpos, float(base), 1.0)[pos]
+        rq, rk = L.apply_rotary_emb(xq, xk, freqs_cis=fc)
+        out[f"c{idx}_cfg"] = np.array([dim, maxpos, base, heads], dtype=np.float64)
+        out[f"c{idx}_cache"] = rot.cos_sin_cache.numpy()                   # float16
+        out[f"c{idx}_pos"] = pos.numpy()
+        for k, v in dict(xq=xq, xk=xk, rq=rq, rk=rk).items():
+            out[f"c{idx}_{k}"] = v.double().numpy()
     np.savez_compressed(os.path.join(HERE, "reference_layer_ops.npz"), **out)
     print("wrote reference_layer_ops.npz", len(out), "arrays")
 

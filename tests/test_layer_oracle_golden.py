@@ -116,3 +116,36 @@ def test_decode_step_is_the_last_row_of_the_prefill(i, ring):
         p = np.exp(s - s.max())
         ref[h] = (p / p.sum()) @ V
     np.testing.assert_allclose(got[0], ref, rtol=5e-6, atol=5e-6 * np.abs(ref).max())
+
+
+N_CACHE = 3
+
+
+@pytest.mark.parametrize("i", range(N_CACHE))
+def test_neox_table_and_rotation_match_the_reference_python(i):
+    """The cos|sin table QuantLlamaRotaryEmbedding builds (fused_attn.py:43-59, fp32 -> fp16) against the oracle's
+    (float64 -> fp16: at most the last bit differs), and the oracle's rotary_embedding_neox on the REFERENCE's table
+    against apply_rotary_emb at the same positions (differs by the table's fp16 rounding only)."""
+    dim, maxpos, base, heads = (int(v) for v in GOLD[f"c{i}_cfg"])
+    cache = GOLD[f"c{i}_cache"].astype(np.float64)
+    assert cache.shape == (maxpos, dim)
+    mine = LO.neox_cos_sin_cache(dim, maxpos, float(base), "f16")
+    # fp32 sin / cos of angles up to maxpos radians carry ~maxpos * 2^-24 of argument error before the fp16 rounding
+    assert np.abs(mine - cache).max() <= 2.0 ** -11 + maxpos * 2.0 ** -23
+    assert (mine != cache).mean() < 0.02
+    pos = GOLD[f"c{i}_pos"]
+    xq, xk = GOLD[f"c{i}_xq"][0], GOLD[f"c{i}_xk"][0]                      # [tokens, heads, dim]
+    rq, rk = LO.rotary_embedding_neox(pos, xq, xk, dim, cache, "f64")
+    for got, want in ((rq, GOLD[f"c{i}_rq"][0]), (rk, GOLD[f"c{i}_rk"][0])):
+        assert np.abs(got - want).max() <= 2 * 2.0 ** -11 * np.abs(want).max() + 1e-6
+
+
+def test_neox_rotation_leaves_the_tail_of_a_head_alone():
+    rng = np.random.default_rng(5)
+    cache = LO.neox_cos_sin_cache(8, 16)                                     # rot_dim 8 < head_size 12
+    q, k = rng.standard_normal((3, 2, 12)), rng.standard_normal((3, 1, 12))
+    rq, rk = LO.rotary_embedding_neox(np.array([1, 15, 0]), q, k, 12, cache, "f64")
+    np.testing.assert_array_equal(rq[..., 8:], q[..., 8:])
+    np.testing.assert_array_equal(rk[..., 8:], k[..., 8:])
+    np.testing.assert_array_equal(rq[2], q[2])                               # position 0: identity
+    assert not np.allclose(rq[0, :, :8], q[0, :, :8])

@@ -81,7 +81,7 @@ def test_unshardable_shapes_are_rejected():
         tp.shard_row(full.qweight, full.scales, full.scaled_zeros, 0, 2)              # 192 k per rank
 
 
-# ------------------------------------------------------------------ world_size-2 gloo run of the modules
+# ------------------------------------------------------------------ world_size 2 and 4 gloo runs of the modules
 def _oracle_local_forward(self, x):
     """Test stand-in for the kernel inside the CPU worker processes."""
     y = O.wq_linear_forward(np64(x), self.qweight.numpy(), np64(self.scales), np64(self.scaled_zeros),
@@ -110,16 +110,19 @@ def _worker(rank, world, port, out_dir):
     y_over = row(hb)
     row.overlap_chunks = 1
     y_one = row(hb)
-    assert y_over.shape == y_one.shape == (700, hidden) and torch.equal(y_over, y_one)
+    assert y_over.shape == y_one.shape == (700, hidden)
+    # two ranks: a + b in either order is the same float; more ranks: the ring's summation order may differ per chunk
+    assert torch.equal(y_over, y_one) if world == 2 else torch.allclose(y_over, y_one, rtol=1e-5, atol=1e-5)
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_column_then_row_parallel_mlp_two_ranks_gloo(tmp_path):
-    world, port = 2, 29500 + os.getpid() % 400
+@pytest.mark.parametrize("world", [2, 4])
+def test_column_then_row_parallel_mlp_gloo(world, tmp_path):
+    port = 29500 + os.getpid() % 400 + world
     mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     ys = [torch.load(os.path.join(tmp_path, f"y{r}.pt")) for r in range(world)]
-    assert torch.equal(ys[0], ys[1])             # every rank holds the reduced result
+    assert all(torch.equal(ys[0], y) for y in ys[1:])   # every rank holds the reduced result
     hidden, inter = 256, 512
     up = _full(inter, hidden, seed=1)
     down = _full(hidden, inter, bias=True, seed=2)

@@ -149,6 +149,71 @@ def layer_ops_golden():
     print("wrote reference_layer_ops.npz", len(out), "arrays")
 
 
+def mlp_callsite_golden():
+    """tests/golden/reference_mlp_callsite.npz: the reference's own, unmodified ``QuantLlamaMLP.our_llama_mlp``
+    (tinychat/modules/fused_mlp.py:36-83) EXECUTED on CPU.  Its two engine calls are served by a stub
+    ``awq_inference_engine`` whose linears are the (separately pinned) W4A16 oracle rounded to fp16; everything the
+    reference does around them -- which branch it takes, the zeros it passes (``- 8 * scales`` in the GEMM branch,
+    :69,76), ``F.silu`` on the fp16 tensor, the fp16 product -- is the reference's code.  Pins
+    oracle/layer_oracle.py::mlp_front (order and placement of the roundings)."""
+    root = os.path.dirname(os.path.dirname(HERE))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    from oracle import w4a16_oracle as O
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    qmodule, _ = _import_reference()
+    eng = sys.modules["awq_inference_engine"]
+    calls = []
+
+    def linear(x, qw, s, z):
+        y = O.wq_linear_forward(x.double().numpy(), qw.numpy(), s.double().numpy(), z.double().numpy(), dtype="f16")
+        return torch.from_numpy(O.rn_f16(y)).to(torch.float16)
+
+    def gemv(x, qw, s, z, m, n, k, g):
+        calls.append(("gemv", m, n, k, g))
+        return linear(x, qw, s, z)
+
+    def gemm(x, qw, s, z):
+        calls.append(("gemm", z.clone()))
+        return linear(x, qw, s, z)
+    eng.gemv_forward_cuda_new, eng.gemm_forward_cuda_new = gemv, gemm
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):
+        import tinychat.modules.fused_mlp as FM
+    g = torch.Generator().manual_seed(606)
+    out = {}
+    for idx, (N, K) in enumerate([(128, 256), (256, 128)]):
+        def layer(n, k):
+            m = qmodule.WQLinear(4, 128, k, n, False, "cpu")
+            q = torch.randint(0, 16, (n, k), generator=g, dtype=torch.int32)
+            m.qweight = qmodule.pack_intweight(q, interleave=4, kstride=64)
+            ng = k // 128
+            sc = (0.004 + 0.01 * torch.rand(ng, n, generator=g)).half()
+            zz = torch.randint(0, 16, (ng, n), generator=g).half()
+            m.scales[:ng] = sc
+            m.scaled_zeros[:ng] = -(sc * zz)
+            return m
+        gate, up, down = layer(N, K), layer(N, K), layer(K, N)
+        mlp = FM.QuantLlamaMLP(gate, down, up)
+        for nm, mod in (("gate", gate), ("up", up)):
+            out[f"m{idx}_{nm}_qweight"] = mod.qweight.numpy()
+            out[f"m{idx}_{nm}_scales"] = mod.scales.float().numpy()
+            out[f"m{idx}_{nm}_szeros"] = mod.scaled_zeros.float().numpy()
+        for tokens in (1, 3, 7, 8, 9, 33):
+            x = (torch.randn(tokens, K, generator=g) * 0.5).half()
+            del calls[:]
+            c = mlp.our_llama_mlp(x)
+            assert len(calls) == 2 and {cc[0] for cc in calls} == ({"gemv"} if tokens < 8 else {"gemm"})
+            out[f"m{idx}_t{tokens}_x"] = x.float().numpy()
+            out[f"m{idx}_t{tokens}_c"] = c.float().numpy()
+            if tokens >= 8:   # the zeros tensors the reference handed to the engine (fp16 arithmetic, :69,76)
+                out[f"m{idx}_t{tokens}_gate_zeros_passed"] = calls[0][1].float().numpy()
+                out[f"m{idx}_t{tokens}_up_zeros_passed"] = calls[1][1].float().numpy()
+    np.savez_compressed(os.path.join(HERE, "reference_mlp_callsite.npz"), **out)
+    print("wrote reference_mlp_callsite.npz", len(out), "arrays")
+
+
 def main():
     qmodule, pseudo_quantize_tensor = _import_reference()
     g = torch.Generator().manual_seed(20260922)
@@ -229,3 +294,4 @@ if __name__ == "__main__":
     main()
     repacker_golden()
     layer_ops_golden()
+    mlp_callsite_golden()

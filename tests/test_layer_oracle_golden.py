@@ -149,3 +149,32 @@ def test_neox_rotation_leaves_the_tail_of_a_head_alone():
     np.testing.assert_array_equal(rk[..., 8:], k[..., 8:])
     np.testing.assert_array_equal(rq[2], q[2])                               # position 0: identity
     assert not np.allclose(rq[0, :, :8], q[0, :, :8])
+
+
+MLP = np.load(os.path.join(HERE, "golden", "reference_mlp_callsite.npz"))
+
+
+@pytest.mark.parametrize("tokens", [1, 3, 7, 8, 9, 33])
+@pytest.mark.parametrize("i", [0, 1])
+def test_mlp_front_matches_the_reference_call_site_executed_on_cpu(i, tokens):
+    """tests/golden/reference_mlp_callsite.npz = the reference's unmodified QuantLlamaMLP.our_llama_mlp run on CPU over
+    oracle-backed engine calls (make_golden.py::mlp_callsite_golden).  mlp_front must reproduce its result: same
+    branch rule (< 8 tokens), same zeros in the GEMM branch (scaled_zeros - 8 * scales in fp16, fused_mlp.py:69,76),
+    roundings in the same places.  torch's fp16 silu goes through fp32, the oracle through float64: a rare last-bit
+    difference of silu is allowed (and then propagates through the product as at most one more ulp)."""
+    from oracle import w4a16_oracle as O
+    x = MLP[f"m{i}_t{tokens}_x"]
+    gate = [MLP[f"m{i}_gate_{k}"] for k in ("qweight", "scales", "szeros")]
+    up = [MLP[f"m{i}_up_{k}"] for k in ("qweight", "scales", "szeros")]
+    if tokens >= 8:
+        for trip, name in ((gate, "gate"), (up, "up")):
+            passed = O.rn_f16(trip[2].astype(np.float64) - O.rn_f16(8.0 * trip[1].astype(np.float64)))
+            np.testing.assert_array_equal(passed, MLP[f"m{i}_t{tokens}_{name}_zeros_passed"].astype(np.float64))
+            trip[2] = passed
+    got = LO.mlp_front(x, gate, up, "f16")
+    want = MLP[f"m{i}_t{tokens}_c"].astype(np.float64)
+    assert got.shape == want.shape
+    diff = np.abs(got - want)
+    ulp = 2.0 ** -10 * np.maximum(np.abs(want), 2.0 ** -14)
+    assert np.all(diff <= 2 * ulp)
+    assert (diff > 0).mean() <= 0.01
